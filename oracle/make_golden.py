@@ -190,7 +190,7 @@ def sphere_incline_random():
         envs.append(dict(qpos0=qpos0.tolist(), qvel0=qvel0.tolist(), e=e, mu=mu, qpos=o["qpos"], qvel=o["qvel"],
                          calls=o["calls"], impulses=o["impulses"], snapshots=o["snapshots"]))
     dump("sphere_incline_random", dict(steps=steps, dt=0.009, thr=0.0, radius=0.2, theta=theta,
-                                       plane_normal=nrm.tolist(), mass=o["mass"], inertia=o["inertia"], envs=envs))
+                                       plane_normal=o["plane_normal"], mass=o["mass"], inertia=o["inertia"], envs=envs))
 
 
 def cube_random():
@@ -217,7 +217,7 @@ def cube_random():
             envs.append(dict(qpos0=qpos0.tolist(), qvel0=qvel0.tolist(), qpos=o["qpos"], qvel=o["qvel"],
                              calls=o["calls"], impulses=o["impulses"], snapshots=o["snapshots"]))
         out[kind] = dict(steps=steps, dt=0.009, thr=1e-4, e=0.2, mu=0.6, half=[0.4, 0.4, 0.4], theta=theta,
-                         plane_normal=nrm.tolist(), mass=o["mass"], inertia=o["inertia"], envs=envs)
+                         plane_normal=o["plane_normal"], mass=o["mass"], inertia=o["inertia"], envs=envs)
     dump("cube_random", out)
 
 
@@ -233,13 +233,13 @@ def general_and_xfrc():
             qpos0 = np.concatenate([p, unit_quat(rng, 1)[0]])
             qvel0 = np.concatenate([rng.uniform(-1, 1, 3), rng.uniform(-3, 3, 3)])
             o = rr.run_single_body("general", xml, qpos0, qvel0, 150, 0.01, 0.7, 0.4, 1e-4, snapshots=SNAP)
-            out["general"].append(dict(geom=geom, size=size, plane_normal=nrm, qpos0=qpos0.tolist(),
+            out["general"].append(dict(geom=geom, size=size, plane_normal=o["plane_normal"], qpos0=qpos0.tolist(),
                                        qvel0=qvel0.tolist(), steps=150, dt=0.01, e=0.7, mu=0.4, thr=1e-4,
                                        mass=o["mass"], inertia=o["inertia"], qpos=o["qpos"], qvel=o["qvel"],
                                        calls=o["calls"], impulses=o["impulses"], snapshots=o["snapshots"]))
             xf = np.concatenate([rng.uniform(-3, 3, 3), rng.uniform(-0.2, 0.2, 3)])
             o = rr.run_single_body("custom", xml, qpos0, qvel0, 150, 0.01, 0.7, 0.4, 0.0, snapshots=SNAP, xfrc=xf)
-            out["xfrc"].append(dict(geom=geom, size=size, plane_normal=nrm, qpos0=qpos0.tolist(),
+            out["xfrc"].append(dict(geom=geom, size=size, plane_normal=o["plane_normal"], qpos0=qpos0.tolist(),
                                     qvel0=qvel0.tolist(), xfrc=xf.tolist(), steps=150, dt=0.01, e=0.7, mu=0.4,
                                     thr=0.0, mass=o["mass"], inertia=o["inertia"], qpos=o["qpos"], qvel=o["qvel"],
                                     calls=o["calls"], impulses=o["impulses"], snapshots=o["snapshots"]))

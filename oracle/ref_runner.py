@@ -188,7 +188,15 @@ def run_single_body(scheme, xml, qpos0, qvel0, steps, dt, restitution, friction,
                                  "calls": counter.calls, "impulses": counter.impulses}
         return {"qpos": data.qpos.tolist(), "qvel": data.qvel.tolist(),
                 "calls": counter.calls, "impulses": counter.impulses, "snapshots": snaps,
-                "mass": float(model.body_mass[-1]), "inertia": model.body_inertia[-1].tolist()}
+                "mass": float(model.body_mass[-1]), "inertia": model.body_inertia[-1].tolist(),
+                "plane_normal": plane_normal_of(mj, model)}
+
+
+def plane_normal_of(mj, model):
+    """The unit normal the fake narrow phase actually uses for the (single) plane geom."""
+    g = [x for x in model.geoms if x.type == "plane"][0]
+    rb = mj._quat_to_mat(model.body_quat[g.body])
+    return (rb @ mj._quat_to_mat(g.quat))[:, 2].tolist() if not (g.quat == [1.0, 0, 0, 0]).all() else rb[:, 2].tolist()
 
 
 def run_multi_sphere(xml, qpos0, qvel0, steps, dt, restitution, friction, snapshots=()):

@@ -1,0 +1,477 @@
+// rbs_capi.cu -- extern "C" boundary of librbsim_b200.so (declared in include/rbsim_b200.h).
+//
+// Argument validation, dtype / template dispatch, launch configuration, error capture and the
+// host-buffer drivers.  Compiled with -fmad=false so that the kernels in rbs_kernels.cuh reproduce
+// the reference's rounding sequence ("strict" arithmetic policy).  There is no CPU fallback: without
+// a usable CUDA device every compute entry point returns RBS_ECUDA.
+#include "rbs_kernels.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "../../include/rbsim_b200.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char *what) {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(RBS_ECUDA, "%s: %s", what, cudaGetErrorString(err));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return RBS_OK;
+}
+
+inline unsigned blocks_for(long n, int block) { return (unsigned)((n + block - 1) / block); }
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+inline bool bad_dtype(int dtype) { return dtype != RBS_F32 && dtype != RBS_F64; }
+inline size_t elem_size(int dtype) { return dtype == RBS_F64 ? sizeof(double) : sizeof(float); }
+
+template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_args *a) {
+    rbs::BodyPlaneParams<T> p;
+    p.n_env = a->n_env;
+    p.stride = a->stride;
+    p.substeps = a->substeps;
+    p.state = static_cast<T *>(a->state);
+    p.mass = static_cast<const T *>(a->mass);
+    p.inertia = static_cast<const T *>(a->inertia);
+    p.size = static_cast<const T *>(a->size);
+    p.rest = static_cast<const T *>(a->restitution);
+    p.fric = static_cast<const T *>(a->friction);
+    p.xfrc = static_cast<const T *>(a->xfrc);
+    p.mass_u = (T)a->mass_u;
+    p.rest_u = (T)a->restitution_u;
+    p.fric_u = (T)a->friction_u;
+    for (int i = 0; i < 3; ++i) {
+        p.inertia_u[i] = (T)a->inertia_u[i];
+        p.size_u[i] = (T)a->size_u[i];
+        p.pp[i] = (T)a->plane_point[i];
+        p.pn[i] = (T)a->plane_normal[i];
+        p.g[i] = (T)a->gravity[i];
+    }
+    p.dt = (T)a->dt;
+    p.thr = (T)a->contact_threshold;
+    p.n_contacts = a->n_contacts;
+    p.n_impulses = a->n_impulses;
+    return p;
+}
+
+template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs_body_plane_args *a) {
+    const rbs::BodyPlaneParams<T> p = make_params<T>(a);
+    const unsigned grid = blocks_for(a->n_env, rbs::kBlock);
+    if (a->inertia_mode == RBS_INERTIA_ISOTROPIC)
+        rbs::step_body_plane_kernel<T, GEOM, SCHEME, 1><<<grid, rbs::kBlock, 0, as_stream(a->stream)>>>(p);
+    else
+        rbs::step_body_plane_kernel<T, GEOM, SCHEME, 0><<<grid, rbs::kBlock, 0, as_stream(a->stream)>>>(p);
+}
+
+template <typename T> void launch_body_plane(const rbs_body_plane_args *a) {
+    if (a->geom == RBS_GEOM_SPHERE) {
+        if (a->scheme == RBS_SCHEME_A) launch_body_plane_iso<T, 0, 0>(a);
+        else launch_body_plane_iso<T, 0, 1>(a);
+    } else {
+        if (a->scheme == RBS_SCHEME_A) launch_body_plane_iso<T, 1, 0>(a);
+        else launch_body_plane_iso<T, 1, 1>(a);
+    }
+}
+
+int validate_body_plane(const rbs_body_plane_args *a, bool need_state) {
+    if (!a) return fail(RBS_EINVAL, "rbs_step_body_plane: null args");
+    if (bad_dtype(a->dtype)) return fail(RBS_EINVAL, "rbs_step_body_plane: dtype %d is not RBS_F32/RBS_F64", a->dtype);
+    if (a->geom != RBS_GEOM_SPHERE && a->geom != RBS_GEOM_BOX) return fail(RBS_EINVAL, "rbs_step_body_plane: bad geom %d", a->geom);
+    if (a->scheme != RBS_SCHEME_A && a->scheme != RBS_SCHEME_GENERAL) return fail(RBS_EINVAL, "rbs_step_body_plane: bad scheme %d", a->scheme);
+    if (a->inertia_mode != RBS_INERTIA_GENERAL && a->inertia_mode != RBS_INERTIA_ISOTROPIC)
+        return fail(RBS_EINVAL, "rbs_step_body_plane: bad inertia_mode %d", a->inertia_mode);
+    if (a->n_env < 0) return fail(RBS_EINVAL, "rbs_step_body_plane: n_env %ld < 0", a->n_env);
+    if (a->substeps < 1) return fail(RBS_EINVAL, "rbs_step_body_plane: substeps %d < 1", a->substeps);
+    if (need_state) {
+        if (a->n_env > 0 && !a->state) return fail(RBS_EINVAL, "rbs_step_body_plane: null state");
+        if (a->stride < a->n_env) return fail(RBS_EINVAL, "rbs_step_body_plane: stride %ld < n_env %ld", a->stride, a->n_env);
+    }
+    if (a->inertia_mode == RBS_INERTIA_ISOTROPIC && !a->inertia &&
+        !(a->inertia_u[0] == a->inertia_u[1] && a->inertia_u[1] == a->inertia_u[2]))
+        return fail(RBS_EINVAL, "rbs_step_body_plane: RBS_INERTIA_ISOTROPIC needs three equal principal moments");
+    return RBS_OK;
+}
+
+template <typename T> rbs::TwoBallParams<T> make_params(const rbs_two_ball_args *a) {
+    rbs::TwoBallParams<T> p;
+    p.n_env = a->n_env;
+    p.stride = a->stride;
+    p.substeps = a->substeps;
+    p.state = static_cast<T *>(a->state);
+    p.mass = static_cast<const T *>(a->mass);
+    p.radius = static_cast<const T *>(a->radius);
+    p.mass_u[0] = (T)a->mass_u[0];
+    p.mass_u[1] = (T)a->mass_u[1];
+    p.radius_u = (T)a->radius_u;
+    for (int i = 0; i < 3; ++i) p.g[i] = (T)a->gravity[i];
+    p.dt = (T)a->dt;
+    p.rest = (T)a->restitution;
+    p.fric = (T)a->friction;
+    p.n_ground = a->n_ground_hits;
+    p.n_pair = a->n_pair_hits;
+    return p;
+}
+
+int validate_two_ball(const rbs_two_ball_args *a, bool need_state) {
+    if (!a) return fail(RBS_EINVAL, "rbs_step_two_ball: null args");
+    if (bad_dtype(a->dtype)) return fail(RBS_EINVAL, "rbs_step_two_ball: dtype %d is not RBS_F32/RBS_F64", a->dtype);
+    if (a->n_env < 0) return fail(RBS_EINVAL, "rbs_step_two_ball: n_env %ld < 0", a->n_env);
+    if (a->substeps < 1) return fail(RBS_EINVAL, "rbs_step_two_ball: substeps %d < 1", a->substeps);
+    if (need_state) {
+        if (a->n_env > 0 && !a->state) return fail(RBS_EINVAL, "rbs_step_two_ball: null state");
+        if (a->stride < a->n_env) return fail(RBS_EINVAL, "rbs_step_two_ball: stride %ld < n_env %ld", a->stride, a->n_env);
+    }
+    return RBS_OK;
+}
+
+template <typename T> rbs::MultiSphereParams<T> make_params(const rbs_multi_sphere_args *a, int env_per_block) {
+    rbs::MultiSphereParams<T> p;
+    p.n_env = a->n_env;
+    p.stride = a->stride;
+    p.substeps = a->substeps;
+    p.n_body = a->n_body;
+    p.env_per_block = env_per_block;
+    p.state = static_cast<T *>(a->state);
+    p.mass = static_cast<const T *>(a->mass);
+    p.inertia = static_cast<const T *>(a->inertia);
+    p.radius = static_cast<const T *>(a->radius);
+    p.mass_u = (T)a->mass_u;
+    p.radius_u = (T)a->radius_u;
+    for (int i = 0; i < 3; ++i) {
+        p.inertia_u[i] = (T)a->inertia_u[i];
+        p.pp[i] = (T)a->plane_point[i];
+        p.pn[i] = (T)a->plane_normal[i];
+        p.g[i] = (T)a->gravity[i];
+    }
+    p.dt = (T)a->dt;
+    p.rest = (T)a->restitution;
+    p.fric = (T)a->friction;
+    p.n_contacts = a->n_contacts;
+    p.n_impulses = a->n_impulses;
+    return p;
+}
+
+int validate_multi_sphere(const rbs_multi_sphere_args *a, bool need_state) {
+    if (!a) return fail(RBS_EINVAL, "rbs_step_multi_sphere: null args");
+    if (bad_dtype(a->dtype)) return fail(RBS_EINVAL, "rbs_step_multi_sphere: dtype %d is not RBS_F32/RBS_F64", a->dtype);
+    if (a->n_body < 1 || a->n_body > 1024) return fail(RBS_EINVAL, "rbs_step_multi_sphere: n_body %d outside 1..1024", a->n_body);
+    if (a->n_env < 0) return fail(RBS_EINVAL, "rbs_step_multi_sphere: n_env %ld < 0", a->n_env);
+    if (a->substeps < 1) return fail(RBS_EINVAL, "rbs_step_multi_sphere: substeps %d < 1", a->substeps);
+    if (a->inertia_mode != RBS_INERTIA_GENERAL && a->inertia_mode != RBS_INERTIA_ISOTROPIC)
+        return fail(RBS_EINVAL, "rbs_step_multi_sphere: bad inertia_mode %d", a->inertia_mode);
+    if (need_state) {
+        if (a->n_env > 0 && !a->state) return fail(RBS_EINVAL, "rbs_step_multi_sphere: null state");
+        if (a->stride < a->n_env * a->n_body)
+            return fail(RBS_EINVAL, "rbs_step_multi_sphere: stride %ld < n_env*n_body %ld", a->stride, a->n_env * a->n_body);
+    }
+    return RBS_OK;
+}
+
+template <typename T> void launch_multi_sphere(const rbs_multi_sphere_args *a) {
+    const int B = a->n_body;
+    int threads = ((B + 31) / 32) * 32;
+    if (threads < 128) threads = 128;
+    const int epb = threads / B;
+    const rbs::MultiSphereParams<T> p = make_params<T>(a, epb);
+    const unsigned grid = (unsigned)((a->n_env + epb - 1) / epb);
+    const size_t smem = (size_t)epb * B * 4 * sizeof(T);
+    if (a->inertia_mode == RBS_INERTIA_ISOTROPIC)
+        rbs::step_multi_sphere_kernel<T, 1><<<grid, threads, smem, as_stream(a->stream)>>>(p);
+    else
+        rbs::step_multi_sphere_kernel<T, 0><<<grid, threads, smem, as_stream(a->stream)>>>(p);
+}
+
+// cached device workspace of the host-buffer drivers -------------------------------------------
+std::mutex g_ws_mutex;
+void *g_ws = nullptr;
+size_t g_ws_bytes = 0;
+
+int workspace(size_t bytes, void **out) {
+    if (bytes > g_ws_bytes) {
+        if (g_ws) cudaFree(g_ws);
+        g_ws = nullptr;
+        g_ws_bytes = 0;
+        cudaError_t err = cudaMalloc(&g_ws, bytes);
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            return fail(err == cudaErrorMemoryAllocation ? RBS_ENOMEM : RBS_ECUDA, "workspace of %zu bytes: %s", bytes,
+                        cudaGetErrorString(err));
+        }
+        g_ws_bytes = bytes;
+    }
+    *out = g_ws;
+    return RBS_OK;
+}
+
+#define RBS_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t err__ = (call);                                                      \
+        if (err__ != cudaSuccess) return fail(RBS_ECUDA, #call ": %s", cudaGetErrorString(err__)); \
+    } while (0)
+
+// shared skeleton of the three host drivers: H2D, pack, step loop, unpack, D2H, sync
+template <typename Args, typename StepFn>
+int run_host(const Args *a, int n_body, int body_fastest, void *qpos_host, void *qvel_host, long total_steps,
+             StepFn step) {
+    if (total_steps < 0) return fail(RBS_EINVAL, "total_steps %ld < 0", total_steps);
+    if (a->n_env == 0) return RBS_OK;
+    if (!qpos_host || !qvel_host) return fail(RBS_EINVAL, "null host buffer");
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    const size_t es = elem_size(a->dtype);
+    const size_t nb = (size_t)a->n_env * n_body;
+    const size_t qpos_bytes = nb * 7 * es, qvel_bytes = nb * 6 * es, state_bytes = nb * 13 * es;
+    void *base = nullptr;
+    int rc = workspace(qpos_bytes + qvel_bytes + state_bytes, &base);
+    if (rc) return rc;
+    char *qpos_d = static_cast<char *>(base), *qvel_d = qpos_d + qpos_bytes, *state_d = qvel_d + qvel_bytes;
+    cudaStream_t stream = as_stream(a->stream);
+    RBS_CUDA(cudaMemcpyAsync(qpos_d, qpos_host, qpos_bytes, cudaMemcpyHostToDevice, stream));
+    RBS_CUDA(cudaMemcpyAsync(qvel_d, qvel_host, qvel_bytes, cudaMemcpyHostToDevice, stream));
+    const long stride = body_fastest ? (long)nb : a->n_env;
+    rc = rbs_pack_state(a->dtype, a->n_env, n_body, body_fastest, qpos_d, qvel_d, state_d, stride, a->stream);
+    if (rc) return rc;
+    Args local = *a;
+    local.state = state_d;
+    local.stride = stride;
+    for (long done = 0; done < total_steps;) {
+        const long k = total_steps - done < a->substeps ? total_steps - done : a->substeps;
+        local.substeps = (int)k;
+        rc = step(&local);
+        if (rc) return rc;
+        done += k;
+    }
+    rc = rbs_unpack_state(a->dtype, a->n_env, n_body, body_fastest, state_d, stride, qpos_d, qvel_d, a->stream);
+    if (rc) return rc;
+    RBS_CUDA(cudaMemcpyAsync(qpos_host, qpos_d, qpos_bytes, cudaMemcpyDeviceToHost, stream));
+    RBS_CUDA(cudaMemcpyAsync(qvel_host, qvel_d, qvel_bytes, cudaMemcpyDeviceToHost, stream));
+    RBS_CUDA(cudaStreamSynchronize(stream));
+    return RBS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rbs_version(void) { return RBS_ABI_VERSION; }
+const char *rbs_last_error(void) { return g_err; }
+unsigned long long rbs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int rbs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rbs_impulse_friction(int dtype, long n, const void *mass, double mass_u, const void *vel, const void *omega,
+                         const void *contact_point, const void *normal, const void *restitution,
+                         double restitution_u, const void *friction, double friction_u, void *out_jn, void *out_jt,
+                         unsigned char *out_flag, void *stream) {
+    if (bad_dtype(dtype)) return fail(RBS_EINVAL, "rbs_impulse_friction: bad dtype %d", dtype);
+    if (n < 0) return fail(RBS_EINVAL, "rbs_impulse_friction: n %ld < 0", n);
+    if (n == 0) return RBS_OK;
+    if (!vel || !omega || !contact_point || !normal || !out_jn || !out_jt) return fail(RBS_EINVAL, "rbs_impulse_friction: null array");
+    const unsigned grid = blocks_for(n, 256);
+    if (dtype == RBS_F64)
+        rbs::impulse_friction_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(
+            n, (const double *)mass, mass_u, (const double *)vel, (const double *)omega, (const double *)contact_point,
+            (const double *)normal, (const double *)restitution, restitution_u, (const double *)friction, friction_u,
+            (double *)out_jn, (double *)out_jt, out_flag);
+    else
+        rbs::impulse_friction_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
+            n, (const float *)mass, (float)mass_u, (const float *)vel, (const float *)omega, (const float *)contact_point,
+            (const float *)normal, (const float *)restitution, (float)restitution_u, (const float *)friction,
+            (float)friction_u, (float *)out_jn, (float *)out_jt, out_flag);
+    return check_launch("rbs_impulse_friction");
+}
+
+int rbs_apply_impulse_friction(int dtype, long n, const void *vel, const void *omega, const void *mass, double mass_u,
+                               const void *inertia_world, const void *contact_point, const void *normal,
+                               const void *jn, const void *jt, void *out_vel, void *out_omega, void *stream) {
+    if (bad_dtype(dtype)) return fail(RBS_EINVAL, "rbs_apply_impulse_friction: bad dtype %d", dtype);
+    if (n < 0) return fail(RBS_EINVAL, "rbs_apply_impulse_friction: n %ld < 0", n);
+    if (n == 0) return RBS_OK;
+    if (!vel || !omega || !inertia_world || !contact_point || !normal || !jn || !jt || !out_vel || !out_omega)
+        return fail(RBS_EINVAL, "rbs_apply_impulse_friction: null array");
+    const unsigned grid = blocks_for(n, 128);
+    if (dtype == RBS_F64)
+        rbs::apply_impulse_kernel<double, 1><<<grid, 128, 0, as_stream(stream)>>>(
+            n, (const double *)vel, (const double *)omega, (const double *)mass, mass_u, (const double *)inertia_world,
+            (const double *)contact_point, (const double *)normal, (const double *)jn, 0.0, (const double *)jt,
+            (double *)out_vel, (double *)out_omega);
+    else
+        rbs::apply_impulse_kernel<float, 1><<<grid, 128, 0, as_stream(stream)>>>(
+            n, (const float *)vel, (const float *)omega, (const float *)mass, (float)mass_u, (const float *)inertia_world,
+            (const float *)contact_point, (const float *)normal, (const float *)jn, 0.0f, (const float *)jt,
+            (float *)out_vel, (float *)out_omega);
+    return check_launch("rbs_apply_impulse_friction");
+}
+
+int rbs_apply_impulse(int dtype, long n, const void *vel, const void *omega, const void *mass, double mass_u,
+                      const void *inertia_world, const void *contact_point, const void *normal, const void *impulse,
+                      double impulse_u, void *out_vel, void *out_omega, void *stream) {
+    if (bad_dtype(dtype)) return fail(RBS_EINVAL, "rbs_apply_impulse: bad dtype %d", dtype);
+    if (n < 0) return fail(RBS_EINVAL, "rbs_apply_impulse: n %ld < 0", n);
+    if (n == 0) return RBS_OK;
+    if (!vel || !omega || !inertia_world || !contact_point || !normal || !out_vel || !out_omega)
+        return fail(RBS_EINVAL, "rbs_apply_impulse: null array");
+    const unsigned grid = blocks_for(n, 128);
+    if (dtype == RBS_F64)
+        rbs::apply_impulse_kernel<double, 0><<<grid, 128, 0, as_stream(stream)>>>(
+            n, (const double *)vel, (const double *)omega, (const double *)mass, mass_u, (const double *)inertia_world,
+            (const double *)contact_point, (const double *)normal, (const double *)impulse, impulse_u, nullptr,
+            (double *)out_vel, (double *)out_omega);
+    else
+        rbs::apply_impulse_kernel<float, 0><<<grid, 128, 0, as_stream(stream)>>>(
+            n, (const float *)vel, (const float *)omega, (const float *)mass, (float)mass_u, (const float *)inertia_world,
+            (const float *)contact_point, (const float *)normal, (const float *)impulse, (float)impulse_u, nullptr,
+            (float *)out_vel, (float *)out_omega);
+    return check_launch("rbs_apply_impulse");
+}
+
+int rbs_inertia_world(int dtype, long n, const void *inertia_diag, const void *quat, void *out, void *stream) {
+    if (bad_dtype(dtype)) return fail(RBS_EINVAL, "rbs_inertia_world: bad dtype %d", dtype);
+    if (n < 0) return fail(RBS_EINVAL, "rbs_inertia_world: n %ld < 0", n);
+    if (n == 0) return RBS_OK;
+    if (!inertia_diag || !quat || !out) return fail(RBS_EINVAL, "rbs_inertia_world: null array");
+    const unsigned grid = blocks_for(n, 256);
+    if (dtype == RBS_F64)
+        rbs::inertia_world_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(n, (const double *)inertia_diag, (const double *)quat, (double *)out);
+    else
+        rbs::inertia_world_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(n, (const float *)inertia_diag, (const float *)quat, (float *)out);
+    return check_launch("rbs_inertia_world");
+}
+
+int rbs_two_ball_impulse(int dtype, long n, const void *mass, double mass_u, const void *inv_inertia,
+                         double inv_inertia_u, const void *v_lin, const void *v_ang, const void *r, const void *normal,
+                         const void *restitution, double restitution_u, const void *friction, double friction_u,
+                         void *out_J, void *stream) {
+    if (bad_dtype(dtype)) return fail(RBS_EINVAL, "rbs_two_ball_impulse: bad dtype %d", dtype);
+    if (n < 0) return fail(RBS_EINVAL, "rbs_two_ball_impulse: n %ld < 0", n);
+    if (n == 0) return RBS_OK;
+    if (!v_lin || !v_ang || !r || !normal || !out_J) return fail(RBS_EINVAL, "rbs_two_ball_impulse: null array");
+    const unsigned grid = blocks_for(n, 256);
+    if (dtype == RBS_F64)
+        rbs::two_ball_impulse_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(
+            n, (const double *)mass, mass_u, (const double *)inv_inertia, inv_inertia_u, (const double *)v_lin,
+            (const double *)v_ang, (const double *)r, (const double *)normal, (const double *)restitution, restitution_u,
+            (const double *)friction, friction_u, (double *)out_J);
+    else
+        rbs::two_ball_impulse_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
+            n, (const float *)mass, (float)mass_u, (const float *)inv_inertia, (float)inv_inertia_u, (const float *)v_lin,
+            (const float *)v_ang, (const float *)r, (const float *)normal, (const float *)restitution, (float)restitution_u,
+            (const float *)friction, (float)friction_u, (float *)out_J);
+    return check_launch("rbs_two_ball_impulse");
+}
+
+int rbs_step_body_plane(const rbs_body_plane_args *a) {
+    int rc = validate_body_plane(a, true);
+    if (rc) return rc;
+    if (a->n_env == 0) return RBS_OK;
+    if (a->dtype == RBS_F64) launch_body_plane<double>(a);
+    else launch_body_plane<float>(a);
+    return check_launch("rbs_step_body_plane");
+}
+
+int rbs_step_two_ball(const rbs_two_ball_args *a) {
+    int rc = validate_two_ball(a, true);
+    if (rc) return rc;
+    if (a->n_env == 0) return RBS_OK;
+    const unsigned grid = blocks_for(a->n_env, rbs::kBlock);
+    if (a->dtype == RBS_F64)
+        rbs::step_two_ball_kernel<double><<<grid, rbs::kBlock, 0, as_stream(a->stream)>>>(make_params<double>(a));
+    else
+        rbs::step_two_ball_kernel<float><<<grid, rbs::kBlock, 0, as_stream(a->stream)>>>(make_params<float>(a));
+    return check_launch("rbs_step_two_ball");
+}
+
+int rbs_step_multi_sphere(const rbs_multi_sphere_args *a) {
+    int rc = validate_multi_sphere(a, true);
+    if (rc) return rc;
+    if (a->n_env == 0) return RBS_OK;
+    if (a->dtype == RBS_F64) launch_multi_sphere<double>(a);
+    else launch_multi_sphere<float>(a);
+    return check_launch("rbs_step_multi_sphere");
+}
+
+int rbs_pack_state(int dtype, long n_env, int n_body, int body_fastest, const void *qpos, const void *qvel,
+                   void *state, long stride, void *stream) {
+    if (bad_dtype(dtype)) return fail(RBS_EINVAL, "rbs_pack_state: bad dtype %d", dtype);
+    if (n_env < 0 || n_body < 1) return fail(RBS_EINVAL, "rbs_pack_state: bad sizes");
+    if (n_env == 0) return RBS_OK;
+    if (!qpos || !qvel || !state) return fail(RBS_EINVAL, "rbs_pack_state: null array");
+    if (stride < (body_fastest ? n_env * n_body : n_env)) return fail(RBS_EINVAL, "rbs_pack_state: stride too small");
+    const unsigned grid = blocks_for(n_env * n_body, 256);
+    if (dtype == RBS_F64)
+        rbs::convert_state_kernel<double, 1><<<grid, 256, 0, as_stream(stream)>>>(n_env, n_body, body_fastest, (double *)qpos, (double *)qvel, (double *)state, stride);
+    else
+        rbs::convert_state_kernel<float, 1><<<grid, 256, 0, as_stream(stream)>>>(n_env, n_body, body_fastest, (float *)qpos, (float *)qvel, (float *)state, stride);
+    return check_launch("rbs_pack_state");
+}
+
+int rbs_unpack_state(int dtype, long n_env, int n_body, int body_fastest, const void *state, long stride, void *qpos,
+                     void *qvel, void *stream) {
+    if (bad_dtype(dtype)) return fail(RBS_EINVAL, "rbs_unpack_state: bad dtype %d", dtype);
+    if (n_env < 0 || n_body < 1) return fail(RBS_EINVAL, "rbs_unpack_state: bad sizes");
+    if (n_env == 0) return RBS_OK;
+    if (!qpos || !qvel || !state) return fail(RBS_EINVAL, "rbs_unpack_state: null array");
+    if (stride < (body_fastest ? n_env * n_body : n_env)) return fail(RBS_EINVAL, "rbs_unpack_state: stride too small");
+    const unsigned grid = blocks_for(n_env * n_body, 256);
+    if (dtype == RBS_F64)
+        rbs::convert_state_kernel<double, 0><<<grid, 256, 0, as_stream(stream)>>>(n_env, n_body, body_fastest, (double *)qpos, (double *)qvel, (double *)state, stride);
+    else
+        rbs::convert_state_kernel<float, 0><<<grid, 256, 0, as_stream(stream)>>>(n_env, n_body, body_fastest, (float *)qpos, (float *)qvel, (float *)state, stride);
+    return check_launch("rbs_unpack_state");
+}
+
+int rbs_run_body_plane_host(const rbs_body_plane_args *a, void *qpos_host, void *qvel_host, long total_steps) {
+    int rc = validate_body_plane(a, false);
+    if (rc) return rc;
+    return run_host(a, 1, 0, qpos_host, qvel_host, total_steps, rbs_step_body_plane);
+}
+
+int rbs_run_two_ball_host(const rbs_two_ball_args *a, void *qpos_host, void *qvel_host, long total_steps) {
+    int rc = validate_two_ball(a, false);
+    if (rc) return rc;
+    return run_host(a, 2, 0, qpos_host, qvel_host, total_steps, rbs_step_two_ball);
+}
+
+int rbs_run_multi_sphere_host(const rbs_multi_sphere_args *a, void *qpos_host, void *qvel_host, long total_steps) {
+    int rc = validate_multi_sphere(a, false);
+    if (rc) return rc;
+    return run_host(a, a->n_body, 1, qpos_host, qvel_host, total_steps, rbs_step_multi_sphere);
+}
+
+int rbs_release_workspace(void) {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    if (g_ws) cudaFree(g_ws);
+    g_ws = nullptr;
+    g_ws_bytes = 0;
+    return RBS_OK;
+}
+
+int rbs_fma_probe(int dtype, long n_threads, int iters, void *sink, void *stream) {
+    if (bad_dtype(dtype)) return fail(RBS_EINVAL, "rbs_fma_probe: bad dtype %d", dtype);
+    if (n_threads <= 0 || n_threads % 256 || iters < 1 || !sink) return fail(RBS_EINVAL, "rbs_fma_probe: n_threads must be a positive multiple of 256");
+    const unsigned grid = (unsigned)(n_threads / 256);
+    if (dtype == RBS_F64) rbs::fma_probe_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(iters, (double *)sink);
+    else rbs::fma_probe_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(iters, (float *)sink);
+    return check_launch("rbs_fma_probe");
+}
+
+}  // extern "C"

@@ -1,0 +1,258 @@
+"""Python side of the steppers: build the C-ABI argument structs from a BatchedModel / BatchedData
+pair and enqueue the CUDA kernels on the current torch stream.  No allocation, no host sync and no
+fallback on the step path: if the CUDA library is absent ``_lib.load()`` raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (RBS_F32, RBS_F64, RBS_GEOM_BOX, RBS_GEOM_SPHERE, RBS_INERTIA_GENERAL, RBS_INERTIA_ISOTROPIC,
+                   RBS_SCHEME_A, RBS_SCHEME_GENERAL, BodyPlaneArgs, MultiSphereArgs, TwoBallArgs)
+
+
+def rbs_dtype(dtype):
+    if dtype == torch.float64:
+        return RBS_F64
+    if dtype == torch.float32:
+        return RBS_F32
+    raise TypeError(f"unsupported dtype {dtype}")
+
+
+def current_stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _per_env_scalar(value, model, n):
+    """A python scalar stays uniform; a tensor / array of n values becomes a device array."""
+    if torch.is_tensor(value) or (isinstance(value, np.ndarray) and value.ndim > 0):
+        t = torch.as_tensor(value, dtype=model.dtype).to(model.device).contiguous()
+        if t.numel() != n:
+            raise ValueError(f"per-environment parameter has {t.numel()} values, expected {n}")
+        return t, 0.0
+    return None, float(value)
+
+
+def _isotropic(inertia):
+    return bool(inertia[0] == inertia[1] == inertia[2])
+
+
+def _require_cuda(model):
+    if model.device.type != "cuda":
+        raise _lib.RbsError("the steppers run on a CUDA device only (no CPU fallback)")
+
+
+def body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold, scheme, substeps,
+                    count=True, strict_inertia=False):
+    """rbs_body_plane_args for the single free body ``body_id`` of ``model`` resting on its plane."""
+    _require_cuda(model)
+    if model.nfree != 1 or data.layout != "env":
+        raise ValueError("this step function handles scenes with exactly one free body (sphere.xml / cube.xml shape)")
+    if model.plane_normal is None:
+        raise ValueError("scene has no plane geom")
+    bid = model.free_ids[0]
+    # the reference indexes body_mass[body_id] with body_id == -1 when the name is absent, i.e. the LAST body
+    # (src/physics/collision.py:58-60 with src/simulation/single_sphere_bounce.py:67)
+    if body_id not in (bid, bid - model.nbody, -1):
+        raise ValueError(f"body id {body_id} is not the free body of this scene")
+    geom = model.body_geom[bid]
+    if geom.type not in ("sphere", "box"):
+        raise ValueError(f"free-body geom type {geom.type!r} has no plane contact routine")
+    a = BodyPlaneArgs()
+    a.dtype = rbs_dtype(model.dtype)
+    a.geom = RBS_GEOM_SPHERE if geom.type == "sphere" else RBS_GEOM_BOX
+    a.scheme = scheme
+    a.n_env, a.stride, a.substeps = data.nenv, data.stride, int(substeps)
+    a.state = _ptr(data.state)
+    pe = model.per_env
+    keep = []                                   # tensors that must outlive the launch
+    mass_t = pe.get("mass")
+    a.mass, a.mass_u = _ptr(mass_t), float(model.body_mass[bid])
+    inertia_t = pe.get("inertia")
+    a.inertia = _ptr(inertia_t)
+    a.inertia_u = _lib.D3(*[float(v) for v in model.body_inertia[bid]])
+    size_t = pe.get("size")
+    a.size = _ptr(size_t)
+    a.size_u = _lib.D3(*[float(v) for v in geom.size])
+    iso = inertia_t is None and _isotropic(model.body_inertia[bid]) and not strict_inertia
+    a.inertia_mode = RBS_INERTIA_ISOTROPIC if iso else RBS_INERTIA_GENERAL
+    # None = "use the per-environment values attached to the model" (randomised configs)
+    rt, ru = _per_env_scalar(pe["restitution"] if restitution is None else restitution, model, data.nenv)
+    ft, fu = _per_env_scalar(pe["friction"] if friction_coeff is None else friction_coeff, model, data.nenv)
+    keep += [rt, ft]
+    a.restitution, a.restitution_u = _ptr(rt), ru
+    a.friction, a.friction_u = _ptr(ft), fu
+    a.xfrc = _ptr(data.xfrc_applied)
+    a.plane_point = _lib.D3(*model.plane_point)
+    a.plane_normal = _lib.D3(*model.plane_normal)
+    a.gravity = _lib.D3(*[float(g) for g in model.opt.gravity])
+    a.dt = float(dt)
+    a.contact_threshold = float(contact_threshold)
+    a.n_contacts = _ptr(data.n_contacts) if count else None
+    a.n_impulses = _ptr(data.n_impulses) if count else None
+    a._keep = keep
+    return a
+
+
+def step_body_plane(model, data, body_id, dt, restitution, friction_coeff, contact_threshold,
+                    scheme=RBS_SCHEME_A, substeps=1, count=True, strict_inertia=False):
+    a = body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold, scheme, substeps,
+                        count, strict_inertia)
+    a.stream = current_stream(model.device)
+    _lib.check(_lib.load().rbs_step_body_plane(ctypes.byref(a)))
+
+
+def two_ball_args(model, data, dt, restitution, friction, radius, substeps, count=True):
+    _require_cuda(model)
+    if model.nfree != 2 or data.layout != "env":
+        raise ValueError("the two-ball step needs a scene with exactly two free bodies (ball_collision.xml shape)")
+    a = TwoBallArgs()
+    a.dtype, a.substeps = rbs_dtype(model.dtype), int(substeps)
+    a.n_env, a.stride = data.nenv, data.stride
+    a.state = _ptr(data.state)
+    pe = model.per_env
+    a.mass = _ptr(pe.get("mass"))                       # [2, E] when per-env
+    a.mass_u = _lib.D2(*[float(model.body_mass[i]) for i in model.free_ids])
+    a.radius, a.radius_u = _ptr(pe.get("radius")), float(radius)
+    a.gravity = _lib.D3(*[float(g) for g in model.opt.gravity])
+    a.dt, a.restitution, a.friction = float(dt), float(restitution), float(friction)
+    a.n_ground_hits = _ptr(data.n_contacts) if count else None
+    a.n_pair_hits = _ptr(data.n_impulses) if count else None
+    return a
+
+
+def step_two_ball(model, data, dt, restitution, friction, radius=0.1, substeps=1, count=True):
+    a = two_ball_args(model, data, dt, restitution, friction, radius, substeps, count)
+    a.stream = current_stream(model.device)
+    _lib.check(_lib.load().rbs_step_two_ball(ctypes.byref(a)))
+
+
+def multi_sphere_args(model, data, dt, restitution, friction, substeps, count=True, strict_inertia=False):
+    _require_cuda(model)
+    if data.layout != "body":
+        raise ValueError("the multi-sphere step needs BatchedData(model, layout='body')")
+    if model.plane_normal is None:
+        raise ValueError("scene has no plane geom")
+    geoms = [model.body_geom[i] for i in model.free_ids]
+    if any(g.type != "sphere" for g in geoms):
+        raise ValueError("the multi-sphere step handles sphere bodies only")
+    pe = model.per_env
+    first = model.free_ids[0]
+    uniform = all(model.body_mass[i] == model.body_mass[first] and geoms[k].size[0] == geoms[0].size[0]
+                  for k, i in enumerate(model.free_ids))
+    if not uniform and not all(k in pe for k in ("mass", "radius", "inertia")):
+        # heterogeneous spheres: expand the per-body values once
+        E, B = data.nenv, data.nfree
+        m = torch.tensor([model.body_mass[i] for i in model.free_ids], dtype=model.dtype, device=model.device)
+        r = torch.tensor([g.size[0] for g in geoms], dtype=model.dtype, device=model.device)
+        I = torch.tensor([model.body_inertia[i] for i in model.free_ids], dtype=model.dtype, device=model.device)
+        pe.setdefault("mass", m.repeat(E).contiguous())
+        pe.setdefault("radius", r.repeat(E).contiguous())
+        pe.setdefault("inertia", I.t().repeat(1, E).contiguous())
+    a = MultiSphereArgs()
+    a.dtype, a.substeps, a.n_body = rbs_dtype(model.dtype), int(substeps), data.nfree
+    a.n_env, a.stride = data.nenv, data.stride
+    a.state = _ptr(data.state)
+    a.mass, a.mass_u = _ptr(pe.get("mass")), float(model.body_mass[first])
+    a.inertia = _ptr(pe.get("inertia"))
+    a.inertia_u = _lib.D3(*[float(v) for v in model.body_inertia[first]])
+    a.radius, a.radius_u = _ptr(pe.get("radius")), float(geoms[0].size[0])
+    a.inertia_mode = RBS_INERTIA_GENERAL if strict_inertia else RBS_INERTIA_ISOTROPIC   # spheres: I1 = I2 = I3
+    a.plane_point = _lib.D3(*model.plane_point)
+    a.plane_normal = _lib.D3(*model.plane_normal)
+    a.gravity = _lib.D3(*[float(g) for g in model.opt.gravity])
+    a.dt, a.restitution, a.friction = float(dt), float(restitution), float(friction)
+    a.n_contacts = _ptr(data.n_contacts) if count else None
+    a.n_impulses = _ptr(data.n_impulses) if count else None
+    return a
+
+
+def step_multi_sphere(model, data, dt, restitution, friction, substeps=1, count=True, strict_inertia=False):
+    a = multi_sphere_args(model, data, dt, restitution, friction, substeps, count, strict_inertia)
+    a.stream = current_stream(model.device)
+    _lib.check(_lib.load().rbs_step_multi_sphere(ctypes.byref(a)))
+
+
+# --------------------------------------------------------------------------------------------------
+# host-buffer drivers (reference layout in, reference layout out)
+# --------------------------------------------------------------------------------------------------
+def _host_ptr(arr, dtype, shape):
+    if torch.is_tensor(arr):
+        if arr.device.type != "cpu" or not arr.is_contiguous() or arr.dtype != dtype or tuple(arr.shape) != shape:
+            raise ValueError(f"host buffer must be a contiguous CPU tensor of {dtype} with shape {shape}")
+        return ctypes.c_void_p(arr.data_ptr())
+    np_dtype = np.float64 if dtype == torch.float64 else np.float32
+    if not (isinstance(arr, np.ndarray) and arr.flags.c_contiguous and arr.dtype == np_dtype and arr.shape == shape):
+        raise ValueError(f"host buffer must be a C-contiguous {np_dtype.__name__} array with shape {shape}")
+    return ctypes.c_void_p(arr.ctypes.data)
+
+
+def run_body_plane_host(model, qpos, qvel, total_steps, body_id=-1, dt=None, restitution=1.0, friction_coeff=1.0,
+                        contact_threshold=0.0, scheme=RBS_SCHEME_A, substeps=32, strict_inertia=False):
+    """Advance host arrays qpos[E,7], qvel[E,6] (in place) by ``total_steps`` steps of A5/A6/A7.
+    H2D, the launches and D2H all happen inside; returns after the stream is synchronised."""
+    data = _HostShim(model, 1)
+    a = body_plane_args(model, data, body_id, model.opt.timestep if dt is None else dt, restitution, friction_coeff,
+                        contact_threshold, scheme, substeps, count=False, strict_inertia=strict_inertia)
+    a.stream = current_stream(model.device)
+    E = model.nenv
+    _lib.check(_lib.load().rbs_run_body_plane_host(ctypes.byref(a), _host_ptr(qpos, model.dtype, (E, 7)),
+                                                   _host_ptr(qvel, model.dtype, (E, 6)), int(total_steps)))
+
+
+def run_two_ball_host(model, qpos, qvel, total_steps, dt=None, restitution=1.0, friction=0.3, radius=0.1, substeps=32):
+    data = _HostShim(model, 2)
+    a = two_ball_args(model, data, model.opt.timestep if dt is None else dt, restitution, friction, radius, substeps,
+                      count=False)
+    a.stream = current_stream(model.device)
+    E = model.nenv
+    _lib.check(_lib.load().rbs_run_two_ball_host(ctypes.byref(a), _host_ptr(qpos, model.dtype, (E, 14)),
+                                                 _host_ptr(qvel, model.dtype, (E, 12)), int(total_steps)))
+
+
+def run_multi_sphere_host(model, qpos, qvel, total_steps, dt=None, restitution=1.0, friction=0.0, substeps=8):
+    data = _HostShim(model, model.nfree, layout="body")
+    a = multi_sphere_args(model, data, model.opt.timestep if dt is None else dt, restitution, friction, substeps,
+                          count=False)
+    a.stream = current_stream(model.device)
+    E, B = model.nenv, model.nfree
+    _lib.check(_lib.load().rbs_run_multi_sphere_host(ctypes.byref(a), _host_ptr(qpos, model.dtype, (E, 7 * B)),
+                                                     _host_ptr(qvel, model.dtype, (E, 6 * B)), int(total_steps)))
+
+
+class _HostShim:
+    """Carries the sizes the *_args builders read from a BatchedData; the host drivers use the library's own
+    device workspace, so no state tensor exists on the Python side."""
+
+    def __init__(self, model, nfree, layout="env"):
+        self.nenv, self.nfree, self.layout = model.nenv, nfree, layout
+        self.stride = model.nenv if layout == "env" else model.nenv * nfree
+        self.state = None
+        self.xfrc_applied = None
+        self.n_contacts = self.n_impulses = None
+
+
+def fma_peak(device, dtype=torch.float64, iters=4096, blocks_per_sm=8):
+    """Measured FMA throughput (FLOP/s) of the CUDA cores of ``device`` for ``dtype`` (bench helper)."""
+    lib = _lib.load()
+    props = torch.cuda.get_device_properties(device)
+    n_threads = props.multi_processor_count * blocks_per_sm * 256
+    sink = torch.empty(n_threads, dtype=dtype, device=device)
+    stream = current_stream(device)
+    code = rbs_dtype(dtype)
+    for _ in range(2):
+        _lib.check(lib.rbs_fma_probe(code, n_threads, iters, _ptr(sink), stream))
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 0.0
+    for _ in range(5):
+        t0.record()
+        _lib.check(lib.rbs_fma_probe(code, n_threads, iters, _ptr(sink), stream))
+        t1.record()
+        t1.synchronize()
+        best = max(best, 2.0 * 8 * n_threads * iters / (t0.elapsed_time(t1) * 1e-3))
+    return best

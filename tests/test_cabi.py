@@ -1,0 +1,65 @@
+"""The C-ABI shared library loads without a GPU and exports exactly what include/rbsim_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rbsim_b200.h")).read()
+    return sorted(set(re.findall(r"RBS_API\s+[\w\s\*]+?\b(rbs_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    from rigidbody_simulation_b200 import _lib
+    assert declared_symbols() == sorted(_lib.PROTOTYPES)
+    assert len(declared_symbols()) == 19
+
+
+def test_library_exports_every_declared_symbol():
+    from rigidbody_simulation_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    loaded = _lib.load()
+    assert loaded.rbs_version() == 1
+    assert loaded.rbs_last_error() is not None
+    assert loaded.rbs_launch_count() >= 0
+
+
+def test_struct_layout_matches_header():
+    """sizeof of the argument structs as the C compiler sees them == ctypes' view."""
+    import subprocess
+    import tempfile
+    from rigidbody_simulation_b200 import _lib
+    src = ('#include <stdio.h>\n#include "rbsim_b200.h"\nint main(void){printf("%zu %zu %zu\\n", sizeof(rbs_body_plane_args),'
+           ' sizeof(rbs_two_ball_args), sizeof(rbs_multi_sphere_args)); return 0;}\n')
+    with tempfile.TemporaryDirectory() as tmp:
+        c = os.path.join(tmp, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(tmp, "t")
+        subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(_lib.BodyPlaneArgs), ctypes.sizeof(_lib.TwoBallArgs), ctypes.sizeof(_lib.MultiSphereArgs)]
+
+
+def test_argument_validation_needs_no_gpu():
+    from rigidbody_simulation_b200 import _lib
+    lib = _lib.load()
+    a = _lib.BodyPlaneArgs()
+    a.dtype = 9
+    assert lib.rbs_step_body_plane(ctypes.byref(a)) == _lib.RBS_EINVAL
+    assert lib.rbs_step_body_plane(None) == _lib.RBS_EINVAL
+    assert lib.rbs_step_two_ball(None) == _lib.RBS_EINVAL
+    m = _lib.MultiSphereArgs()
+    m.dtype, m.n_body, m.substeps = 1, 4096, 1
+    assert lib.rbs_step_multi_sphere(ctypes.byref(m)) == _lib.RBS_EINVAL and b"n_body" in lib.rbs_last_error()
+    assert lib.rbs_impulse_friction(5, 1, None, 1.0, None, None, None, None, None, 1.0, None, 0.5, None, None, None, None) == _lib.RBS_EINVAL
+    with pytest.raises(ValueError):
+        _lib.check(_lib.RBS_EINVAL)

@@ -1,0 +1,198 @@
+"""CPU tests of the host-side logic: XML subset parser against the values the (fake) MuJoCo compiler gives
+the reference, the index-keyed synthetic generator, sharding, config mirror, and the no-fallback rule."""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_parser_matches_reference_model_values(golden):
+    from rigidbody_simulation_b200 import mjcf, scenes
+    mv = golden("model_values")
+    for name in ("sphere", "cube", "ball_collision", "multi_sphere"):
+        sc = mjcf.parse_file(scenes.model_path(name))
+        ref = mv[name]
+        assert [b.name for b in sc.bodies] == ref["body_names"]
+        assert [b.mass for b in sc.bodies] == ref["body_mass"]                  # bit-for-bit
+        assert [b.inertia for b in sc.bodies] == ref["body_inertia"]
+        assert sc.gravity == ref["gravity"] and sc.timestep == ref["timestep"]
+        qpos0 = []
+        for i in sc.free_bodies:
+            qpos0 += sc.bodies[i].pos + sc.bodies[i].quat
+        assert qpos0 == ref["qpos0"]
+        _, normal = mjcf.plane_frame(sc, sc.planes()[0])
+        assert normal == ref["plane_normal"]
+    sc = mjcf.parse_file(scenes.model_path("sphere"))
+    assert sc.body_id("sphere") == -1 and sc.body_id("ball") == 2           # the reference relies on the -1
+    # the reference's own XML files parse to the same numbers (only where the checkout exists)
+    ref_models = "/root/reference/models"
+    if os.path.isdir(ref_models):
+        for name in ("sphere", "cube", "ball_collision", "multi_sphere"):
+            a, b = mjcf.parse_file(os.path.join(ref_models, name + ".xml")), mjcf.parse_file(scenes.model_path(name))
+            assert [x.mass for x in a.bodies] == [x.mass for x in b.bodies]
+            assert [x.pos + x.quat for x in a.bodies] == [x.pos + x.quat for x in b.bodies]
+            assert a.timestep == b.timestep and a.gravity == b.gravity
+
+
+def test_parser_templating_and_errors():
+    from rigidbody_simulation_b200 import mjcf
+    txt = ('<mujoco><option gravity="0 0 -9.8" timestep="{TIMESTEP}"/><worldbody>'
+           '<geom type="plane" size="1 1 1" euler="{INCLINE_ANGLE} 0 0"/>'
+           '<body name="b" pos="0 0 1"><freejoint/><geom type="box" size="0.3 0.2 0.1" density="50"/></body>'
+           '</worldbody></mujoco>')
+    sc = mjcf.parse_string(mjcf.render_template(txt, incline_angle=0.25, timestep=0.004))
+    assert sc.timestep == 0.004
+    _, n = mjcf.plane_frame(sc, sc.planes()[0])
+    assert n == pytest.approx([0, -math.sin(0.25), math.cos(0.25)], abs=1e-15)
+    m = 50 * 8 * 0.3 * 0.2 * 0.1
+    assert sc.bodies[1].mass == pytest.approx(m, rel=1e-15)
+    assert sc.bodies[1].inertia == pytest.approx([m / 3 * (0.04 + 0.01), m / 3 * (0.09 + 0.01), m / 3 * (0.09 + 0.04)], rel=1e-14)
+    with pytest.raises(ValueError):
+        mjcf.parse_string('<mujoco><worldbody><geom type="capsule" size="1 1"/></worldbody></mujoco>')
+    with pytest.raises(ValueError):
+        mjcf.parse_string('<mujoco><compiler angle="degree"/><worldbody/></mujoco>')
+    with pytest.raises(ValueError):
+        mjcf.parse_string("<notmujoco/>")
+
+
+def test_synth_is_keyed_by_global_index():
+    from rigidbody_simulation_b200 import synth
+    from rigidbody_simulation_b200.shard import shard_range
+    whole = synth.sphere_incline(1001)
+    parts = [synth.sphere_incline(c, start=s) for s, c in (shard_range(1001, r, 4) for r in range(4))]
+    assert (np.concatenate([p["qpos"] for p in parts]) == whole["qpos"]).all()
+    assert (np.concatenate([p["friction"] for p in parts]) == whole["friction"]).all()
+    q = whole["qpos"][:, 3:7]
+    assert np.allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-15)
+    h = whole["qpos"][:, :3] @ whole["plane_normal"]
+    assert h.min() >= 0.25 - 1e-12 and h.max() <= 2.5 + 1e-12              # starts above the plane
+    assert 0.5 <= whole["restitution"].min() and whole["restitution"].max() < 1.0
+    assert synth.sphere_incline(10, seed=1)["qpos"].tolist() != whole["qpos"][:10].tolist()
+    ms = synth.multi_sphere(3, n_body=64)
+    assert ms["qpos"].shape == (3, 448) and ms["qvel"].shape == (3, 384)
+    tb = synth.two_ball(5)
+    assert tb["qpos"].shape == (5, 14) and (tb["qpos"][:, 3] == 1).all()
+    for kind in ("bounce", "incline"):
+        c = synth.cube(7, kind=kind)
+        assert np.allclose(np.linalg.norm(c["qpos"][:, 3:7], axis=1), 1.0, atol=1e-15)
+    u = synth.uniform01(1, 2, np.arange(100000))
+    assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 5e-3
+
+
+def test_shard_ranges_partition():
+    from rigidbody_simulation_b200.shard import shard_range
+    for n, w in ((1 << 20, 8), (65536, 8), (10, 4), (3, 8), (0, 2)):
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+        for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+            assert s0 + c0 == s1
+        assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 4, 4)
+
+
+def test_config_mirror_matches_reference_values():
+    sys.path.insert(0, os.path.join(ROOT, "rigidbody-simulation_b200"))
+    try:
+        from rigidbody_simulation_b200.src.config import load_sim_config
+    finally:
+        sys.path.pop(0)
+    c = load_sim_config("cube_incline")
+    assert (c["FRICTION_COEFFICIENT"], c["RESTITUTION"], c["TIMESTEP"], c["INCLINE_ANGLE_RAD"]) == (0.6, 0.2, 0.009, 0.7)
+    assert load_sim_config("single_sphere_bounce")["RESTITUTION"] == 1.0
+    assert load_sim_config("ball_collision")["FRICTION_COEFFICIENT"] == 0.3
+    assert load_sim_config("multi_sphere_bounce")["FRICTION_COEFFICIENT"] == 0.0
+    d = load_sim_config("unknown")
+    assert (d["FRICTION_COEFFICIENT"], d["RESTITUTION"], d["TIMESTEP"], d["INCLINE_ANGLE_RAD"]) == (0.5, 0.9, 0.01, 0.0)
+    assert set(d) == {"FRICTION_COEFFICIENT", "RESTITUTION", "TIMESTEP", "INCLINE_ANGLE_RAD", "RECORD_VIDEO", "CAMERA", "RECORDING_PATH"}
+
+
+def test_reference_module_paths_importable():
+    """`src.physics.collision` etc. resolve to the drop-in when rigidbody-simulation_b200/ is on sys.path."""
+    code = ("import sys; sys.path.insert(0, 'rigidbody-simulation_b200');"
+            "from src.physics.collision import compute_collision_impulse_friction, compute_inertia_tensor_world, "
+            "custom_step_with_impulse_collision_friction, apply_impulse, apply_impulse_friction;"
+            "from src.physics.physics_utils import apply_impulse, apply_impulse_friction;"
+            "from src.physics.time_integeration import timestep_integration, general, compute_inertia_tensor_world;"
+            "from src.simulation.ball_collision import compute_inverse_inertia, compute_collision_impulse, step_with_custom_collisions;"
+            "from src.simulation.multi_sphere_bounce import custom_step_multi_sphere;"
+            "from src.simulate import run_simulation, main;"
+            "from src.config import load_sim_config;"
+            "import inspect;"
+            "s = inspect.signature(custom_step_with_impulse_collision_friction);"
+            "assert list(s.parameters)[:7] == ['model','obj','data','dt','restitution','friction_coeff','contact_threshold'];"
+            "assert [s.parameters[k].default for k in ('dt','restitution','friction_coeff','contact_threshold')] == [0.01,1.0,1.0,0];"
+            "s = inspect.signature(timestep_integration);"
+            "assert [s.parameters[k].default for k in ('dt','restitution','friction_coeff','contact_threshold')] == [0.01,1.0,0.5,1e-4];"
+            "s = inspect.signature(general);"
+            "assert [s.parameters[k].default for k in ('dt','restitution','friction_coeff','contact_threshold')] == [0.01,1.0,0.5,1e-4];"
+            "print('ok')")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
+
+
+def test_cli_unknown_name_exits_1():
+    code = ("import sys; sys.path.insert(0, 'rigidbody-simulation_b200');"
+            "from src.simulate import main; main(['--sim', 'nope'])")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 1 and "Unknown simulation name" in r.stdout
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to run instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for GPU-less hosts")
+    import rigidbody_simulation_b200 as rb
+    from rigidbody_simulation_b200 import scenes, stepper
+    with pytest.raises(rb.RbsError):
+        rb.compute_collision_impulse_friction(1.0, None, np.zeros(3), np.zeros(3), np.zeros(3), np.array([0, 0, 1.0]), 1.0, 0.5)
+    model = rb.BatchedModel.from_xml_path(scenes.model_path("sphere"), nenv=4, device="cpu")
+    data = rb.BatchedData(model)
+    with pytest.raises(rb.RbsError):
+        stepper.step_body_plane(model, data, -1, 0.009, 1.0, 0.5, 0.0)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under the product package may reference it."""
+    pkg = os.path.join(ROOT, "rigidbody-simulation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "c_oracle" not in text and "pyport" not in text and "rb_oracle" not in text, f
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_batched_data_views_on_cpu():
+    """AoS views over the SoA state (device-independent logic, exercised on CPU tensors)."""
+    import torch
+    import rigidbody_simulation_b200 as rb
+    from rigidbody_simulation_b200 import scenes
+    m1 = rb.BatchedModel.from_xml_path(scenes.model_path("sphere"), nenv=1, device="cpu")
+    d1 = rb.BatchedData(m1)
+    assert d1.qpos.shape == (7,) and np.asarray(d1.qpos).tolist() == [0, 0, 2.0, 1, 0, 0, 0]
+    d1.qvel[3:6] = np.array([2.0, 2.0, 0.0])
+    assert d1.qvel[3:6].tolist() == [2.0, 2.0, 0.0] and isinstance(d1.qvel[:3], np.ndarray)
+    for layout, name in (("env", "ball_collision"), ("body", "multi_sphere")):
+        m = rb.BatchedModel.from_xml_path(scenes.model_path(name), nenv=5, device="cpu")
+        d = rb.BatchedData(m, layout=layout)
+        B = m.nfree
+        qp = np.arange(5 * 7 * B, dtype=np.float64).reshape(5, 7 * B)
+        qv = -np.arange(5 * 6 * B, dtype=np.float64).reshape(5, 6 * B)
+        d.set_state(qp, qv)
+        assert (d.qpos.torch().numpy() == qp).all() and (d.qvel.torch().numpy() == qv).all()
+        assert d.qpos[2, 7:10].tolist() == qp[2, 7:10].tolist()
+        d.qvel[:, 0:3] = 0.0
+        assert (d.qvel.torch().numpy()[:, 0:3] == 0).all() and (d.qvel.torch().numpy()[:, 3:] == qv[:, 3:]).all()
+        mask = torch.tensor([True, False, False, True, False])
+        d.reset(mask)
+        q = d.qpos.torch().numpy()
+        assert (q[0] == m.qpos0).all() and (q[1] == qp[1]).all() and (d.qvel.torch().numpy()[3] == 0).all()
+        d.reset()
+        assert (d.qpos.torch().numpy() == m.qpos0).all()
