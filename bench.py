@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on B200: batched sphere-on-incline stepping (BASELINE config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over one batch: advance all E environments of this rank by
+``--substeps`` integration steps (default 2048, the throughput horizon of SURVEY.md section 8(d)), issued as
+launches of ``--fuse`` fused substeps.  Metric: env-substeps/s, whole job (all ranks), device-timed with CUDA
+events, max over ranks.  Prints ONE JSON line on rank 0 ("Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-substeps/s"
+ENVS_PER_GPU = 1 << 20
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
+    p.add_argument("--substeps", type=int, default=2048, help="integration steps per bench step")
+    p.add_argument("--fuse", type=int, default=64, help="substeps fused per kernel launch")
+    p.add_argument("--dtype", default="fp64", choices=["fp64", "fp32"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-envs-per-core", type=int, default=16)
+    p.add_argument("--cpu-steps", type=int, default=400)
+    p.add_argument("--k1-launches", type=int, default=64, help="launches per step of the 1-substep-per-launch regime")
+    return p.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "sphere_incline_1M: models/sphere.xml body (r=0.2, density 50) over a plane tilted 0.7 rad, "
+                        "randomised pose/velocity, per-env restitution U(0.5,1) and friction U(0,1), dt=0.009 "
+                        "(BASELINE configs[1])",
+            "envs_per_gpu": args.envs, "envs_total": args.envs * n_gpus, "substeps_per_step": args.substeps,
+            "substeps_fused_per_launch": args.fuse, "sharding": f"env-sharded x{n_gpus}, no collective on the step path",
+            "l2": "L2 flushed (512 MiB write) between timed steps"}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def reference_arm(args):
+    """The reference's own CPU implementation of the path on the box's host cores.  The reference is a Python
+    package that cannot travel to this box, so its step function is timed through the NumPy port in oracle/
+    (same NumPy/SciPy calls, fake MuJoCo for contacts), one process per core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_baseline
+    from rigidbody_simulation_b200 import synth
+    cores = os.cpu_count() or 1
+    sample = synth.sphere_incline(cores * args.cpu_envs_per_core)
+    values, walls = [], []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline.python_port_sphere_incline(sample, cores, args.cpu_envs_per_core, args.cpu_steps)
+        if i >= args.warmup:
+            values.append(r["value"])
+            walls.append(r["wall_s"])
+    v = sum(values) / len(values)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": v, "unit": METRIC, "cores": cores, "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": v, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.samples, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [s.split(", ") for t, s in self.samples if t0 <= t <= t1] or [s.split(", ") for _, s in self.samples[-3:]]
+        sm = sorted(float(r[1]) for r in rows if len(r) > 8)
+        reasons = set()
+        for r in rows:
+            if len(r) > 8:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.strip() == "Active":
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][2]) if rows and len(rows[0]) > 2 else None,
+                "power_w_max": max((float(r[3]) for r in rows if len(r) > 8), default=None), "samples": len(rows),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def b200_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import rigidbody_simulation_b200 as rb
+    from rigidbody_simulation_b200 import scenes, shard, stepper, synth
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rb._lib.load()
+    tdtype = torch.float64 if args.dtype == "fp64" else torch.float32
+    esize = 8 if args.dtype == "fp64" else 4
+    E, S, F = args.envs, args.substeps, args.fuse
+    if S % F:
+        raise SystemExit("--substeps must be a multiple of --fuse")
+
+    # CPU baseline first (rank 0, before the timed GPU region so the host is quiet during it)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import cpu_baseline
+        cores = os.cpu_count() or 1
+        sample = synth.sphere_incline(cores * args.cpu_envs_per_core)
+        cpu = cpu_baseline.python_port_sphere_incline(sample, cores, args.cpu_envs_per_core, args.cpu_steps)
+        try:
+            cpu_native = cpu_baseline.c_port_sphere_incline(synth.sphere_incline(1 << 16), steps=200)
+        except Exception as exc:                              # the native port is informative only
+            cpu_native = {"error": str(exc)}
+
+    # this rank's shard of the global environment index space (weak scaling: E per GPU)
+    s = synth.sphere_incline(E, start=rank * E)
+    model = scenes.sphere_on_incline(E, device=dev, dtype=tdtype)
+    model.set_per_env(restitution=s["restitution"], friction=s["friction"])
+    data = rb.BatchedData(model)
+    qpos_h = torch.from_numpy(s["qpos"]).to(tdtype).pin_memory()
+    qvel_h = torch.from_numpy(s["qvel"]).to(tdtype).pin_memory()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def reset_state():
+        data.set_state(qpos_h, qvel_h)
+
+    def one_step(fuse):
+        for _ in range(S // fuse):
+            stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=fuse, count=False)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        t0 = time.time()
+        for a, b in evs:
+            flush.fill_(1)                                   # evict L2 between timed steps
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        t1 = time.time()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        return shard.max_over_ranks(ms, dev), t0, t1
+
+    # --- device-resident throughput (inputs already in HBM) -------------------------------------------
+    reset_state()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = rb.launch_count()
+    total_ms, t0, t1 = timed(lambda: one_step(F), args.steps, args.warmup)
+    launches = rb.launch_count() - launches0 - args.warmup * (S // F)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = world * E * S / (ms_per_step * 1e-3)
+
+    # --- contact statistics of the timed regime (untimed, counters on) for the algorithmic flop count ----
+    data.n_contacts.zero_()
+    data.n_impulses.zero_()
+    stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=F, count=True)
+    torch.cuda.synchronize(dev)
+    c_per = float(data.n_contacts.sum().item()) / (E * F)
+    i_per = float(data.n_impulses.sum().item()) / (E * F)
+
+    # --- K=1 streaming regime (HBM-bound): one launch per substep ---------------------------------------
+    k1_launches = args.k1_launches
+
+    def k1_step():
+        for _ in range(k1_launches):
+            stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=1, count=False)
+
+    k1_ms, _, _ = timed(k1_step, max(3, args.steps), 3)
+    k1_launch_ms = k1_ms / max(3, args.steps) / k1_launches
+
+    # --- end to end through the host-buffer C-ABI call (H2D + S substeps + D2H every step) --------------
+    def e2e_step():
+        stepper.run_body_plane_host(model, qpos_h, qvel_h, S, dt=s["dt"], restitution=None, friction_coeff=None,
+                                    contact_threshold=0.0, substeps=F)
+
+    e2e_ms, _, _ = timed(e2e_step, args.steps, args.warmup)
+    e2e_value = world * E * S / (e2e_ms / args.steps * 1e-3)
+
+    # --- roofline ----------------------------------------------------------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    fp_peak = stepper.fma_peak(dev, tdtype) / 1e12           # TFLOP/s, FMA = 2 flops, measured on this device
+    # algorithmic work per env-substep (DESIGN.md "Measurement"): free flight 60 flops (4 div, 1 sqrt incl.),
+    # + 104 per contact handed to the impulse routine that produces an impulse; state 13+13 scalars and the two
+    # per-env parameters (restitution, friction) cross HBM once per launch.
+    flops_per_substep = 60.0 + 104.0 * i_per + 12.0 * (c_per - i_per)
+    bytes_per_launch = E * (26 + 2) * esize
+    launch_ms = ms_per_step / (S // F)
+    fused_tflops = E * F * flops_per_substep / (launch_ms * 1e-3) / 1e12
+    fused_gbs = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+    k1_gbs = bytes_per_launch / (k1_launch_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.dtype == "fp64" else "f32", "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": E * 13 * esize,
+                    "d2h_bytes_per_step": E * 13 * esize, "ms_per_step": e2e_ms / args.steps,
+                    "call": "rbs_run_body_plane_host via stepper.run_body_plane_host (pinned host qpos/qvel in the "
+                            "reference layout)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "fp64" if args.dtype == "fp64" else "fp32", "kernel": "rbs::step_body_plane_kernel<T,sphere,schemeA,iso>",
+                         "achieved": fused_tflops, "peak": fp_peak, "unit": "TFLOP/s", "frac": fused_tflops / fp_peak,
+                         "peak_source": "FMA microbenchmark rbs_fma_probe run in this process (MEASURED_PEAKS.json has no "
+                                        "CUDA-core peak)",
+                         "flops_per_env_substep": flops_per_substep, "contacts_per_env_substep": c_per,
+                         "impulses_per_env_substep": i_per, "launch_ms": launch_ms, "substeps_per_launch": F,
+                         "hbm_GBps_of_same_launch": fused_gbs, "traffic": None},
+            "roofline_k1": {"bound": "hbm", "kernel": "same kernel, 1 substep per launch (the reference's per-frame call)",
+                            "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
+                            "peak_source": hbm_src, "bytes_per_env": (26 + 2) * esize, "launch_ms": k1_launch_ms,
+                            "env_steps_per_s": world * E / (k1_launch_ms * 1e-3), "traffic": None},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline_native"] = cpu_native
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "../../include/rbsim_b200.h"
@@ -67,13 +68,31 @@ template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_a
     return p;
 }
 
+// Resident CTAs per SM the headline kernel is compiled for (register cap 65536 / (128 * MINB)).
+// Measured on B200, 1M envs fp64 (profiles/r1_tuning.md): fused launches are fastest at 6 (80 regs), the
+// one-substep streaming launch at 8 (64 regs, more loads in flight).  RBS_MINB overrides for experiments.
+int tuning_minb(int substeps) {
+    static int forced = [] { const char *e = getenv("RBS_MINB"); return e ? atoi(e) : 0; }();
+    if (forced) return forced;
+    return substeps <= 2 ? 8 : 6;
+}
+
 template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs_body_plane_args *a) {
     const rbs::BodyPlaneParams<T> p = make_params<T>(a);
     const unsigned grid = blocks_for(a->n_env, rbs::kBlock);
-    if (a->inertia_mode == RBS_INERTIA_ISOTROPIC)
-        rbs::step_body_plane_kernel<T, GEOM, SCHEME, 1><<<grid, rbs::kBlock, 0, as_stream(a->stream)>>>(p);
-    else
-        rbs::step_body_plane_kernel<T, GEOM, SCHEME, 0><<<grid, rbs::kBlock, 0, as_stream(a->stream)>>>(p);
+    cudaStream_t st = as_stream(a->stream);
+    if (a->inertia_mode == RBS_INERTIA_ISOTROPIC) {
+        if (GEOM == 0 && SCHEME == 0) {      // occupancy variants of the headline kernel
+            switch (tuning_minb(a->substeps)) {
+                case 6: rbs::step_body_plane_kernel<T, GEOM, SCHEME, 1, 6><<<grid, rbs::kBlock, 0, st>>>(p); return;
+                case 8: rbs::step_body_plane_kernel<T, GEOM, SCHEME, 1, 8><<<grid, rbs::kBlock, 0, st>>>(p); return;
+                default: break;
+            }
+        }
+        rbs::step_body_plane_kernel<T, GEOM, SCHEME, 1, 4><<<grid, rbs::kBlock, 0, st>>>(p);
+    } else {
+        rbs::step_body_plane_kernel<T, GEOM, SCHEME, 0, 2><<<grid, rbs::kBlock, 0, st>>>(p);
+    }
 }
 
 template <typename T> void launch_body_plane(const rbs_body_plane_args *a) {

@@ -396,7 +396,7 @@ def test_substep_fusion_and_shard_invariance_1m(rb):
     assert float((qn - 1).abs().max()) < 1e-14
     assert torch.isfinite(ref).all()
     calls, imps = whole.counters()
-    assert calls.sum() > E and (imps <= calls).all()
+    assert calls.sum() > E // 2 and (imps <= calls).all()
 
 
 def test_shard_generator_is_index_keyed():
