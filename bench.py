@@ -31,8 +31,10 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     p.add_argument("--substeps", type=int, default=2048, help="integration steps per bench step")
-    p.add_argument("--fuse", type=int, default=64, help="substeps fused per kernel launch")
+    p.add_argument("--fuse", type=int, default=128, help="substeps fused per kernel launch")
     p.add_argument("--dtype", default="fp64", choices=["fp64", "fp32"])
+    p.add_argument("--arith", default="fast", choices=["strict", "fast"],
+                   help="strict = the reference's rounding sequence; fast = FMA/reciprocal re-association (<=1e-12/step)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-envs-per-core", type=int, default=16)
     p.add_argument("--cpu-steps", type=int, default=400)
@@ -45,7 +47,7 @@ def workload_config(args, n_gpus):
                         "randomised pose/velocity, per-env restitution U(0.5,1) and friction U(0,1), dt=0.009 "
                         "(BASELINE configs[1])",
             "envs_per_gpu": args.envs, "envs_total": args.envs * n_gpus, "substeps_per_step": args.substeps,
-            "substeps_fused_per_launch": args.fuse, "sharding": f"env-sharded x{n_gpus}, no collective on the step path",
+            "substeps_fused_per_launch": args.fuse, "arith": args.arith, "sharding": f"env-sharded x{n_gpus}, no collective on the step path",
             "l2": "L2 flushed (512 MiB write) between timed steps"}
 
 
@@ -167,7 +169,7 @@ def b200_arm(args):
 
     def one_step(fuse):
         for _ in range(S // fuse):
-            stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=fuse, count=False)
+            stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=fuse, count=False, arith=args.arith)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -204,10 +206,22 @@ def b200_arm(args):
     ms_per_step = total_ms / args.steps
     value = world * E * S / (ms_per_step * 1e-3)
 
+    # --- the other arithmetic policy, same job, for the record ------------------------------------------------
+    other = "strict" if args.arith == "fast" else "fast"
+
+    def other_step():
+        for _ in range(S // F):
+            stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=F, count=False, arith=other)
+
+    reset_state()
+    other_ms, _, _ = timed(other_step, max(2, args.steps // 2), 1)
+    other_value = world * E * S / (other_ms / max(2, args.steps // 2) * 1e-3)
+    reset_state()
+
     # --- contact statistics of the timed regime (untimed, counters on) for the algorithmic flop count ----
     data.n_contacts.zero_()
     data.n_impulses.zero_()
-    stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=F, count=True)
+    stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=F, count=True, arith=args.arith)
     torch.cuda.synchronize(dev)
     c_per = float(data.n_contacts.sum().item()) / (E * F)
     i_per = float(data.n_impulses.sum().item()) / (E * F)
@@ -217,7 +231,7 @@ def b200_arm(args):
 
     def k1_step():
         for _ in range(k1_launches):
-            stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=1, count=False)
+            stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=1, count=False, arith=args.arith)
 
     k1_ms, _, _ = timed(k1_step, max(3, args.steps), 3)
     k1_launch_ms = k1_ms / max(3, args.steps) / k1_launches
@@ -225,7 +239,7 @@ def b200_arm(args):
     # --- end to end through the host-buffer C-ABI call (H2D + S substeps + D2H every step) --------------
     def e2e_step():
         stepper.run_body_plane_host(model, qpos_h, qvel_h, S, dt=s["dt"], restitution=None, friction_coeff=None,
-                                    contact_threshold=0.0, substeps=F)
+                                    contact_threshold=0.0, substeps=F, arith=args.arith)
 
     e2e_ms, _, _ = timed(e2e_step, args.steps, args.warmup)
     e2e_value = world * E * S / (e2e_ms / args.steps * 1e-3)
@@ -240,10 +254,11 @@ def b200_arm(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     fp_peak = stepper.fma_peak(dev, tdtype) / 1e12           # TFLOP/s, FMA = 2 flops, measured on this device
-    # algorithmic work per env-substep (DESIGN.md "Measurement"): free flight 60 flops (4 div, 1 sqrt incl.),
-    # + 104 per contact handed to the impulse routine that produces an impulse; state 13+13 scalars and the two
+    # algorithmic work per env-substep: free flight 60 flops (incl. 4 div, 1 sqrt);
+    # +72 per contact that produces an impulse, +22 per contact found separating (u_n >= 0); mul/add/div/sqrt = 1
+    # flop each, i.e. an FMA-capable pipe could retire two of them per lane-cycle.  State 13+13 scalars and the two
     # per-env parameters (restitution, friction) cross HBM once per launch.
-    flops_per_substep = 60.0 + 104.0 * i_per + 12.0 * (c_per - i_per)
+    flops_per_substep = 60.0 + 72.0 * i_per + 22.0 * (c_per - i_per)
     bytes_per_launch = E * (26 + 2) * esize
     launch_ms = ms_per_step / (S // F)
     fused_tflops = E * F * flops_per_substep / (launch_ms * 1e-3) / 1e12
@@ -273,6 +288,10 @@ def b200_arm(args):
                             "peak_source": hbm_src, "bytes_per_env": (26 + 2) * esize, "launch_ms": k1_launch_ms,
                             "env_steps_per_s": world * E / (k1_launch_ms * 1e-3), "traffic": None},
         }
+        line["other_policy"] = {"arith": other, "value": other_value, "unit": METRIC,
+                                "note": "strict = the reference's rounding sequence, bit-for-bit the C oracle on "
+                                        "inertia-free paths; fast = FMA / reciprocal-multiply re-association, <= 1e-12 "
+                                        "relative per step and exact contact-event counts (tests/test_gpu_parity.py)"}
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline_native"] = cpu_native

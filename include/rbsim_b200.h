@@ -46,6 +46,7 @@ enum { RBS_F32 = 0, RBS_F64 = 1 };
 enum { RBS_GEOM_SPHERE = 0, RBS_GEOM_BOX = 1 };
 enum { RBS_SCHEME_A = 0, RBS_SCHEME_GENERAL = 1 };
 enum { RBS_INERTIA_GENERAL = 0, RBS_INERTIA_ISOTROPIC = 1 };
+enum { RBS_ARITH_STRICT = 0, RBS_ARITH_FAST = 1 };
 enum { RBS_OK = 0, RBS_EINVAL = -1, RBS_ECUDA = -2, RBS_ENOMEM = -3 };
 
 RBS_API int rbs_version(void);
@@ -107,7 +108,9 @@ typedef struct rbs_body_plane_args {
     long n_env;
     long stride;               /* elements between state rows, >= n_env */
     int substeps;              /* >= 1 */
-    int reserved;
+    int arith;                 /* RBS_ARITH_STRICT: the reference's rounding sequence (bit-faithful);
+                                  RBS_ARITH_FAST: FMA / reciprocal-multiply re-association, <= 1e-12 per step in
+                                  fp64; implemented for sphere + scheme A + isotropic inertia */
     void *state;               /* [13][stride], env-major, n_body = 1 */
     const void *mass;          double mass_u;
     const void *inertia;       double inertia_u[3];   /* [3][n_env] body-frame principal moments */

@@ -15,6 +15,7 @@ RBS_F32, RBS_F64 = 0, 1
 RBS_GEOM_SPHERE, RBS_GEOM_BOX = 0, 1
 RBS_SCHEME_A, RBS_SCHEME_GENERAL = 0, 1
 RBS_INERTIA_GENERAL, RBS_INERTIA_ISOTROPIC = 0, 1
+RBS_ARITH_STRICT, RBS_ARITH_FAST = 0, 1
 RBS_OK, RBS_EINVAL, RBS_ECUDA, RBS_ENOMEM = 0, -1, -2, -3
 
 D3 = c_double * 3
@@ -25,7 +26,7 @@ class BodyPlaneArgs(Structure):
     """struct rbs_body_plane_args"""
     _fields_ = [
         ("dtype", c_int), ("geom", c_int), ("scheme", c_int), ("inertia_mode", c_int),
-        ("n_env", c_long), ("stride", c_long), ("substeps", c_int), ("reserved", c_int),
+        ("n_env", c_long), ("stride", c_long), ("substeps", c_int), ("arith", c_int),
         ("state", c_void_p),
         ("mass", c_void_p), ("mass_u", c_double),
         ("inertia", c_void_p), ("inertia_u", D3),

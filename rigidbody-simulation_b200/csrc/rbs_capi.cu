@@ -68,12 +68,14 @@ template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_a
     return p;
 }
 
-// Resident CTAs per SM the headline kernel is compiled for (register cap 65536 / (128 * MINB)).
-// Measured on B200, 1M envs fp64 (profiles/r1_tuning.md): fused launches are fastest at 6 (80 regs), the
-// one-substep streaming launch at 8 (64 regs, more loads in flight).  RBS_MINB overrides for experiments.
-int tuning_minb(int substeps) {
+// Resident CTAs per SM the headline kernels are compiled for (register cap 65536 / (128 * MINB)).
+// Measured on B200, 1M envs fp64 (profiles/r1_summary.md): strict policy -- fused launches fastest at 6 (80 regs),
+// the one-substep streaming launch at 8 (64 regs, more loads in flight); fast policy -- fused at 4, streaming at 6.
+// RBS_MINB overrides for experiments.
+int tuning_minb(int substeps, int arith) {
     static int forced = [] { const char *e = getenv("RBS_MINB"); return e ? atoi(e) : 0; }();
     if (forced) return forced;
+    if (arith == RBS_ARITH_FAST) return substeps <= 2 ? 6 : 4;
     return substeps <= 2 ? 8 : 6;
 }
 
@@ -83,7 +85,7 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
     cudaStream_t st = as_stream(a->stream);
     if (a->inertia_mode == RBS_INERTIA_ISOTROPIC) {
         if (GEOM == 0 && SCHEME == 0) {      // occupancy variants of the headline kernel
-            switch (tuning_minb(a->substeps)) {
+            switch (tuning_minb(a->substeps, RBS_ARITH_STRICT)) {
                 case 6: rbs::step_body_plane_kernel<T, GEOM, SCHEME, 1, 6><<<grid, rbs::kBlock, 0, st>>>(p); return;
                 case 8: rbs::step_body_plane_kernel<T, GEOM, SCHEME, 1, 8><<<grid, rbs::kBlock, 0, st>>>(p); return;
                 default: break;
@@ -95,7 +97,19 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
     }
 }
 
+template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a) {
+    const rbs::BodyPlaneParams<T> p = make_params<T>(a);
+    const unsigned grid = blocks_for(a->n_env, rbs::kBlock);
+    cudaStream_t st = as_stream(a->stream);
+    switch (tuning_minb(a->substeps, RBS_ARITH_FAST)) {
+        case 4: rbs::step_sphere_plane_fast_kernel<T, 4><<<grid, rbs::kBlock, 0, st>>>(p); break;
+        case 6: rbs::step_sphere_plane_fast_kernel<T, 6><<<grid, rbs::kBlock, 0, st>>>(p); break;
+        default: rbs::step_sphere_plane_fast_kernel<T, 8><<<grid, rbs::kBlock, 0, st>>>(p); break;
+    }
+}
+
 template <typename T> void launch_body_plane(const rbs_body_plane_args *a) {
+    if (a->arith == RBS_ARITH_FAST) return launch_sphere_plane_fast<T>(a);
     if (a->geom == RBS_GEOM_SPHERE) {
         if (a->scheme == RBS_SCHEME_A) launch_body_plane_iso<T, 0, 0>(a);
         else launch_body_plane_iso<T, 0, 1>(a);
@@ -112,6 +126,10 @@ int validate_body_plane(const rbs_body_plane_args *a, bool need_state) {
     if (a->scheme != RBS_SCHEME_A && a->scheme != RBS_SCHEME_GENERAL) return fail(RBS_EINVAL, "rbs_step_body_plane: bad scheme %d", a->scheme);
     if (a->inertia_mode != RBS_INERTIA_GENERAL && a->inertia_mode != RBS_INERTIA_ISOTROPIC)
         return fail(RBS_EINVAL, "rbs_step_body_plane: bad inertia_mode %d", a->inertia_mode);
+    if (a->arith != RBS_ARITH_STRICT && a->arith != RBS_ARITH_FAST) return fail(RBS_EINVAL, "rbs_step_body_plane: bad arith %d", a->arith);
+    if (a->arith == RBS_ARITH_FAST &&
+        !(a->geom == RBS_GEOM_SPHERE && a->scheme == RBS_SCHEME_A && a->inertia_mode == RBS_INERTIA_ISOTROPIC))
+        return fail(RBS_EINVAL, "rbs_step_body_plane: RBS_ARITH_FAST is implemented for sphere + scheme A + isotropic inertia only");
     if (a->n_env < 0) return fail(RBS_EINVAL, "rbs_step_body_plane: n_env %ld < 0", a->n_env);
     if (a->substeps < 1) return fail(RBS_EINVAL, "rbs_step_body_plane: substeps %d < 1", a->substeps);
     if (need_state) {

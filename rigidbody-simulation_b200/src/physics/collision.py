@@ -28,12 +28,12 @@ def _position(data):
 
 
 def custom_step_with_impulse_collision_friction(model, obj, data, dt=0.01, restitution=1.0, friction_coeff=1.0,
-                                                contact_threshold=0, substeps=1):
+                                                contact_threshold=0, substeps=1, arith="strict"):
     """One step of scheme A for every environment in ``data`` (in place), reference lines :56-102:
     contacts of the start-of-step pose, gravity / applied wrench, sequential per-contact impulses
     (normal + Coulomb-clamped tangential), then position and first-order quaternion integration."""
     mj.mj_forward(model, data)                                              # :57 (contacts are generated in-kernel)
     body_id = mj.mj_name2id(model, mj.mjtObj.mjOBJ_BODY, f"{obj}")          # :58 (-1 -> last body, as shipped)
     stepper.step_body_plane(model, data, body_id, dt, restitution, friction_coeff, contact_threshold,
-                            scheme=RBS_SCHEME_A, substeps=substeps)
+                            scheme=RBS_SCHEME_A, substeps=substeps, arith=arith)
     return _position(data)

@@ -47,8 +47,11 @@ def _require_cuda(model):
         raise _lib.RbsError("the steppers run on a CUDA device only (no CPU fallback)")
 
 
+ARITH = {"strict": _lib.RBS_ARITH_STRICT, "fast": _lib.RBS_ARITH_FAST}
+
+
 def body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold, scheme, substeps,
-                    count=True, strict_inertia=False):
+                    count=True, strict_inertia=False, arith="strict"):
     """rbs_body_plane_args for the single free body ``body_id`` of ``model`` resting on its plane."""
     _require_cuda(model)
     if model.nfree != 1 or data.layout != "env":
@@ -67,6 +70,7 @@ def body_plane_args(model, data, body_id, dt, restitution, friction_coeff, conta
     a.dtype = rbs_dtype(model.dtype)
     a.geom = RBS_GEOM_SPHERE if geom.type == "sphere" else RBS_GEOM_BOX
     a.scheme = scheme
+    a.arith = ARITH[arith]
     a.n_env, a.stride, a.substeps = data.nenv, data.stride, int(substeps)
     a.state = _ptr(data.state)
     pe = model.per_env
@@ -100,9 +104,11 @@ def body_plane_args(model, data, body_id, dt, restitution, friction_coeff, conta
 
 
 def step_body_plane(model, data, body_id, dt, restitution, friction_coeff, contact_threshold,
-                    scheme=RBS_SCHEME_A, substeps=1, count=True, strict_inertia=False):
+                    scheme=RBS_SCHEME_A, substeps=1, count=True, strict_inertia=False, arith="strict"):
+    """arith: "strict" reproduces the reference's rounding sequence; "fast" re-associates for the FP pipe
+    (sphere + scheme A + isotropic inertia only; <= 1e-12 relative per step in fp64)."""
     a = body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold, scheme, substeps,
-                        count, strict_inertia)
+                        count, strict_inertia, arith)
     a.stream = current_stream(model.device)
     _lib.check(_lib.load().rbs_step_body_plane(ctypes.byref(a)))
 
@@ -193,12 +199,12 @@ def _host_ptr(arr, dtype, shape):
 
 
 def run_body_plane_host(model, qpos, qvel, total_steps, body_id=-1, dt=None, restitution=1.0, friction_coeff=1.0,
-                        contact_threshold=0.0, scheme=RBS_SCHEME_A, substeps=32, strict_inertia=False):
+                        contact_threshold=0.0, scheme=RBS_SCHEME_A, substeps=32, strict_inertia=False, arith="strict"):
     """Advance host arrays qpos[E,7], qvel[E,6] (in place) by ``total_steps`` steps of A5/A6/A7.
     H2D, the launches and D2H all happen inside; returns after the stream is synchronised."""
     data = _HostShim(model, 1)
     a = body_plane_args(model, data, body_id, model.opt.timestep if dt is None else dt, restitution, friction_coeff,
-                        contact_threshold, scheme, substeps, count=False, strict_inertia=strict_inertia)
+                        contact_threshold, scheme, substeps, count=False, strict_inertia=strict_inertia, arith=arith)
     a.stream = current_stream(model.device)
     E = model.nenv
     _lib.check(_lib.load().rbs_run_body_plane_host(ctypes.byref(a), _host_ptr(qpos, model.dtype, (E, 7)),

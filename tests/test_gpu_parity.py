@@ -215,7 +215,7 @@ def test_shipped_single_sphere_and_cube_scripts(rb, golden):
     assert (int(calls.sum()), int(imps.sum())) == (957, 723)
 
 
-def _oracle_vs_gpu_single(rb, geom, kind_fn, E, steps, dtype, strict):
+def _oracle_vs_gpu_single(rb, geom, kind_fn, E, steps, dtype, strict, arith="strict"):
     from rigidbody_simulation_b200 import stepper, synth
     s = kind_fn(E)
     size = [s["radius"]] if geom == "sphere" else s["half"]
@@ -234,7 +234,7 @@ def _oracle_vs_gpu_single(rb, geom, kind_fn, E, steps, dtype, strict):
     for upto in (1, steps):
         co.step_body_plane(qp, qv, upto - done, **okw)
         stepper.step_body_plane(model, data, -1, s["dt"], None, None, s["threshold"], substeps=upto - done,
-                                strict_inertia=strict)
+                                strict_inertia=strict, arith=arith)
         done = upto
         gq, gv = state_of(data)
         out[upto] = (max(comp_rel_err(gq, qp, 1e-3), comp_rel_err(gv, qv, 1e-3)),
@@ -255,6 +255,46 @@ def test_sphere_incline_100k_vs_oracle(rb, dtype, tol):
             assert out[200][0] <= 1e-9, out
         if strict:                           # literal inertia path: same rounding sequence as the oracle
             assert out[1][1] == 1.0 and out[1][2] == 1.0, out
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, F64_STEP), (np.float32, F32_STEP)])
+def test_sphere_incline_fast_policy_vs_oracle(rb, dtype, tol):
+    """The re-associated ("fast") arithmetic policy meets the same bar: one step <= tolerance, and in fp64 the
+    contact-event counts over the horizon are exactly the oracle's."""
+    from rigidbody_simulation_b200 import synth
+    out, counts_ok, ncalls = _oracle_vs_gpu_single(rb, "sphere", lambda E: synth.sphere_incline(E), 200_000, 300, dtype,
+                                                   False, arith="fast")
+    assert out[1][0] <= tol, out
+    assert ncalls > 200_000
+    if dtype == np.float64:
+        assert counts_ok
+        assert out[300][0] <= 1e-6, out        # measured divergence: 6e-15 @1, 2e-12 @10, 4e-11 @100, 1e-8 @300 steps
+
+
+def test_fast_policy_golden_and_scope(rb, golden):
+    from rigidbody_simulation_b200 import stepper
+    from rigidbody_simulation_b200.src.physics.collision import custom_step_with_impulse_collision_friction as step
+    g = golden("sphere_incline_random")
+    envs = g["envs"]
+    model, data = make_single(rb, "sphere", [g["radius"]], g["theta"], col(envs, "qpos0"), col(envs, "qvel0"))
+    model.set_per_env(restitution=col(envs, "e"), friction=col(envs, "mu"))
+    devs = _step_snapshots(model, data, g, envs, step, restitution=None, friction_coeff=None, contact_threshold=g["thr"],
+                           arith="fast")
+    assert devs[1] <= F64_STEP and devs[g["steps"]] <= 1e-7, devs
+    calls, imps = data.counters()
+    assert (calls[:, 0] == col(envs, "calls")).all() and (imps[:, 0] == col(envs, "impulses")).all()
+    # shipped single-sphere script (config 1) under the fast policy: same counts, same trajectory to 1e-9
+    s = golden("script_single_sphere_2000")
+    model, data = make_single(rb, "sphere", [0.2], 0.0, np.array([s["qpos0"]]), np.array([s["qvel0"]]))
+    step(model, "obj", data, dt=0.009, restitution=1.0, friction_coeff=0.5, substeps=2000, arith="fast")
+    calls, imps = data.counters()
+    assert (int(calls.sum()), int(imps.sum())) == (131, 125)
+    assert np.max(np.abs(np.asarray(data.qpos) - s["qpos"])) < 1e-9
+    # the policy exists for the headline kernel only; anything else is refused, not silently strict
+    c = golden("cube_random")["bounce"]
+    model, data = make_single(rb, "box", c["half"], 0.0, col(c["envs"], "qpos0"), col(c["envs"], "qvel0"))
+    with pytest.raises(ValueError):
+        stepper.step_body_plane(model, data, -1, 0.009, 0.2, 0.6, 1e-4, arith="fast")
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, F64_STEP), (np.float32, F32_STEP)])
