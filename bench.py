@@ -82,41 +82,51 @@ def reference_arm(args):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons every ~5 ms through NVML while the timed region runs."""
 
     def __init__(self, gpu_index):
-        self.samples, self.proc, self.gpu = [], None, gpu_index
+        self.samples, self.gpu, self._stop, self._thread, self.err = [], gpu_index, False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as exc:                      # NVML missing: report that, never fake numbers
+            self.err = repr(exc)
+            return
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append((time.time(), line.strip()))
+    def _run(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((time.time(), sm, pw, rs))
+            except Exception as exc:
+                self.err = repr(exc)
+                return
+            time.sleep(0.005)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [s.split(", ") for t, s in self.samples if t0 <= t <= t1] or [s.split(", ") for _, s in self.samples[-3:]]
-        sm = sorted(float(r[1]) for r in rows if len(r) > 8)
-        reasons = set()
-        for r in rows:
-            if len(r) > 8:
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if val.strip() == "Active":
-                        reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][2]) if rows and len(rows[0]) > 2 else None,
-                "power_w_max": max((float(r[3]) for r in rows if len(r) > 8), default=None), "samples": len(rows),
-                "reasons": sorted(reasons)}
+        self._stop = True
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable: %s" % self.err]}
+        nv = self.nv
+        rows = [x for x in self.samples if t0 <= x[0] <= t1] or self.samples[-3:]
+        sm = sorted(r[1] for r in rows)
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if any(r[3] & bit for r in rows))
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_sm, "power_w_max": max(r[2] for r in rows),
+                "samples": len(rows), "reasons": reasons}
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
@@ -198,25 +208,13 @@ def b200_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.05)
     launches0 = rb.launch_count()
     total_ms, t0, t1 = timed(lambda: one_step(F), args.steps, args.warmup)
     launches = rb.launch_count() - launches0 - args.warmup * (S // F)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = world * E * S / (ms_per_step * 1e-3)
-
-    # --- the other arithmetic policy, same job, for the record ------------------------------------------------
-    other = "strict" if args.arith == "fast" else "fast"
-
-    def other_step():
-        for _ in range(S // F):
-            stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=F, count=False, arith=other)
-
-    reset_state()
-    other_ms, _, _ = timed(other_step, max(2, args.steps // 2), 1)
-    other_value = world * E * S / (other_ms / max(2, args.steps // 2) * 1e-3)
-    reset_state()
 
     # --- contact statistics of the timed regime (untimed, counters on) for the algorithmic flop count ----
     data.n_contacts.zero_()
@@ -225,6 +223,17 @@ def b200_arm(args):
     torch.cuda.synchronize(dev)
     c_per = float(data.n_contacts.sum().item()) / (E * F)
     i_per = float(data.n_impulses.sum().item()) / (E * F)
+
+    # --- the other arithmetic policy, same job, continuing from the same (steady-state) regime ------------------
+    other = "strict" if args.arith == "fast" else "fast"
+
+    def other_step():
+        for _ in range(S // F):
+            stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=F, count=False, arith=other)
+
+    n_other = max(2, args.steps // 2)
+    other_ms, _, _ = timed(other_step, n_other, 1)
+    other_value = world * E * S / (other_ms / n_other * 1e-3)
 
     # --- K=1 streaming regime (HBM-bound): one launch per substep ---------------------------------------
     k1_launches = args.k1_launches
@@ -276,7 +285,7 @@ def b200_arm(args):
                             "reference layout)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp64" if args.dtype == "fp64" else "fp32", "kernel": "rbs::step_body_plane_kernel<T,sphere,schemeA,iso>",
+            "roofline": {"bound": "fp64" if args.dtype == "fp64" else "fp32", "kernel": ("rbs::step_sphere_plane_fast_kernel<double>" if args.arith == "fast" else "rbs::step_body_plane_kernel<double,sphere,schemeA,iso>") if args.dtype == "fp64" else "float instantiation of the same kernel",
                          "achieved": fused_tflops, "peak": fp_peak, "unit": "TFLOP/s", "frac": fused_tflops / fp_peak,
                          "peak_source": "FMA microbenchmark rbs_fma_probe run in this process (MEASURED_PEAKS.json has no "
                                         "CUDA-core peak)",
@@ -302,6 +311,14 @@ def b200_arm(args):
 
 def main():
     args = parse()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: `python bench.py --gpus N` re-launches itself under torchrun, one rank per GPU
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                  "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
     if args.impl == "reference":
         reference_arm(args)
     else:

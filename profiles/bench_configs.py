@@ -1,0 +1,78 @@
+"""Throughput of every BASELINE config at its stated size (device-timed, CUDA events, state resident in HBM).
+Not the bench line (that is config 2, bench.py) -- a record of where the other steppers stand.
+    python profiles/bench_configs.py [--quick]
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import rigidbody_simulation_b200 as rb
+from rigidbody_simulation_b200 import scenes, stepper, synth
+from rigidbody_simulation_b200.src.simulation import ball_collision, multi_sphere_bounce
+
+quick = "--quick" in sys.argv
+dev = torch.device("cuda:0")
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+
+def timed(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    ms = []
+    for _ in range(reps):
+        flush.fill_(0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); b.synchronize()
+        ms.append(a.elapsed_time(b))
+    return float(np.median(ms))
+
+
+def report(name, E, B, K, ms, extra=""):
+    print(json.dumps({"config": name, "envs": E, "bodies_per_env": B, "substeps_per_launch": K, "launch_ms": round(ms, 4),
+                      "env_substeps_per_s": E * K / (ms * 1e-3), "body_substeps_per_s": E * B * K / (ms * 1e-3), "note": extra}), flush=True)
+
+
+for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
+    E = (1 << 20) if not quick else (1 << 16)
+    # config 2 (both policies) --------------------------------------------------------------------------------
+    s = synth.sphere_incline(E)
+    model = scenes.sphere_on_incline(E, device=dev, dtype=dtype)
+    model.set_per_env(restitution=s["restitution"], friction=s["friction"])
+    data = rb.BatchedData(model)
+    data.set_state(s["qpos"], s["qvel"])
+    for arith in ("strict", "fast"):
+        for K in (1, 128):
+            f = lambda: stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=K, count=False, arith=arith)
+            for _ in range(8):
+                stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=128, count=False, arith=arith)
+            report(f"cfg2 sphere_incline {tag} {arith}", E, 1, K, timed(f))
+    # config 4 cube ------------------------------------------------------------------------------------------
+    for kind in ("bounce", "incline"):
+        s = synth.cube(E, kind=kind)
+        model = scenes.cube_on_plane(E, theta=s["theta"], device=dev, dtype=dtype)
+        data = rb.BatchedData(model)
+        data.set_state(s["qpos"], s["qvel"])
+        for K in (1, 64):
+            f = lambda: stepper.step_body_plane(model, data, -1, s["dt"], 0.2, 0.6, 1e-4, substeps=K, count=False)
+            report(f"cfg4 cube_{kind} {tag} strict", E, 1, K, timed(f))
+    # config 3 two balls ---------------------------------------------------------------------------------------
+    s = synth.two_ball(E)
+    model, data = ball_collision.build(E, device=dev, dtype=dtype)
+    data.set_state(s["qpos"], s["qvel"])
+    for K in (1, 64):
+        f = lambda: stepper.step_two_ball(model, data, 0.01, 1.0, 0.3, radius=0.1, substeps=K, count=False)
+        report(f"cfg3 two_ball {tag} strict", E, 2, K, timed(f))
+    # config 5 multi sphere (8192 envs = the per-GPU shard of 65536 over 8 GPUs; and the whole 65536) ------------
+    for E5 in ((8192, 65536) if not quick else (1024,)):
+        s = synth.multi_sphere(E5, n_body=64, friction=0.0)
+        model, data = multi_sphere_bounce.build(E5, device=dev, dtype=dtype, n_body=64)
+        data.set_state(s["qpos"], s["qvel"])
+        for K in (1, 16):
+            f = lambda: stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.0, substeps=K, count=False)
+            report(f"cfg5 multi_sphere64 {tag} strict", E5, 64, K, timed(f, reps=3, warm=1))

@@ -101,10 +101,14 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
     const rbs::BodyPlaneParams<T> p = make_params<T>(a);
     const unsigned grid = blocks_for(a->n_env, rbs::kBlock);
     cudaStream_t st = as_stream(a->stream);
+    if (a->xfrc) {
+        rbs::step_sphere_plane_fast_kernel<T, 4, true><<<grid, rbs::kBlock, 0, st>>>(p);
+        return;
+    }
     switch (tuning_minb(a->substeps, RBS_ARITH_FAST)) {
-        case 4: rbs::step_sphere_plane_fast_kernel<T, 4><<<grid, rbs::kBlock, 0, st>>>(p); break;
-        case 6: rbs::step_sphere_plane_fast_kernel<T, 6><<<grid, rbs::kBlock, 0, st>>>(p); break;
-        default: rbs::step_sphere_plane_fast_kernel<T, 8><<<grid, rbs::kBlock, 0, st>>>(p); break;
+        case 4: rbs::step_sphere_plane_fast_kernel<T, 4, false><<<grid, rbs::kBlock, 0, st>>>(p); break;
+        case 6: rbs::step_sphere_plane_fast_kernel<T, 6, false><<<grid, rbs::kBlock, 0, st>>>(p); break;
+        default: rbs::step_sphere_plane_fast_kernel<T, 8, false><<<grid, rbs::kBlock, 0, st>>>(p); break;
     }
 }
 
