@@ -39,18 +39,31 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 inline bool bad_dtype(int dtype) { return dtype != RBS_F32 && dtype != RBS_F64; }
 inline size_t elem_size(int dtype) { return dtype == RBS_F64 ? sizeof(double) : sizeof(float); }
 
-template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_args *a) {
+// A launch may cover a window [off, off+cnt) of the environments described by `a` (the host-buffer driver
+// pipelines chunks); per-env parameter arrays keep their full-size row stride.
+struct Window {
+    long off, cnt;
+    void *state;
+    long stride;
+    cudaStream_t stream;
+};
+
+inline Window whole(const rbs_body_plane_args *a) { return {0, a->n_env, a->state, a->stride, as_stream(a->stream)}; }
+
+template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_args *a, const Window &w) {
     rbs::BodyPlaneParams<T> p;
-    p.n_env = a->n_env;
-    p.stride = a->stride;
+    auto at = [&](const void *base) { return base ? static_cast<const T *>(base) + w.off : nullptr; };
+    p.n_env = w.cnt;
+    p.stride = w.stride;
+    p.pstride = a->n_env;
     p.substeps = a->substeps;
-    p.state = static_cast<T *>(a->state);
-    p.mass = static_cast<const T *>(a->mass);
-    p.inertia = static_cast<const T *>(a->inertia);
-    p.size = static_cast<const T *>(a->size);
-    p.rest = static_cast<const T *>(a->restitution);
-    p.fric = static_cast<const T *>(a->friction);
-    p.xfrc = static_cast<const T *>(a->xfrc);
+    p.state = static_cast<T *>(w.state);
+    p.mass = at(a->mass);
+    p.inertia = at(a->inertia);
+    p.size = at(a->size);
+    p.rest = at(a->restitution);
+    p.fric = at(a->friction);
+    p.xfrc = at(a->xfrc);
     p.mass_u = (T)a->mass_u;
     p.rest_u = (T)a->restitution_u;
     p.fric_u = (T)a->friction_u;
@@ -63,8 +76,8 @@ template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_a
     }
     p.dt = (T)a->dt;
     p.thr = (T)a->contact_threshold;
-    p.n_contacts = a->n_contacts;
-    p.n_impulses = a->n_impulses;
+    p.n_contacts = a->n_contacts ? a->n_contacts + w.off : nullptr;
+    p.n_impulses = a->n_impulses ? a->n_impulses + w.off : nullptr;
     return p;
 }
 
@@ -79,10 +92,10 @@ int tuning_minb(int substeps, int arith) {
     return substeps <= 2 ? 8 : 6;
 }
 
-template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs_body_plane_args *a) {
-    const rbs::BodyPlaneParams<T> p = make_params<T>(a);
-    const unsigned grid = blocks_for(a->n_env, rbs::kBlock);
-    cudaStream_t st = as_stream(a->stream);
+template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs_body_plane_args *a, const Window &w) {
+    const rbs::BodyPlaneParams<T> p = make_params<T>(a, w);
+    const unsigned grid = blocks_for(w.cnt, rbs::kBlock);
+    cudaStream_t st = w.stream;
     if (a->inertia_mode == RBS_INERTIA_ISOTROPIC) {
         if (GEOM == 0 && SCHEME == 0) {      // occupancy variants of the headline kernel
             switch (tuning_minb(a->substeps, RBS_ARITH_STRICT)) {
@@ -97,10 +110,10 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
     }
 }
 
-template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a) {
-    const rbs::BodyPlaneParams<T> p = make_params<T>(a);
-    const unsigned grid = blocks_for(a->n_env, rbs::kBlock);
-    cudaStream_t st = as_stream(a->stream);
+template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a, const Window &w) {
+    const rbs::BodyPlaneParams<T> p = make_params<T>(a, w);
+    const unsigned grid = blocks_for(w.cnt, rbs::kBlock);
+    cudaStream_t st = w.stream;
     if (a->xfrc) {
         rbs::step_sphere_plane_fast_kernel<T, 4, true><<<grid, rbs::kBlock, 0, st>>>(p);
         return;
@@ -112,15 +125,21 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
     }
 }
 
-template <typename T> void launch_body_plane(const rbs_body_plane_args *a) {
-    if (a->arith == RBS_ARITH_FAST) return launch_sphere_plane_fast<T>(a);
+template <typename T> void launch_body_plane(const rbs_body_plane_args *a, const Window &w) {
+    if (a->arith == RBS_ARITH_FAST) return launch_sphere_plane_fast<T>(a, w);
     if (a->geom == RBS_GEOM_SPHERE) {
-        if (a->scheme == RBS_SCHEME_A) launch_body_plane_iso<T, 0, 0>(a);
-        else launch_body_plane_iso<T, 0, 1>(a);
+        if (a->scheme == RBS_SCHEME_A) launch_body_plane_iso<T, 0, 0>(a, w);
+        else launch_body_plane_iso<T, 0, 1>(a, w);
     } else {
-        if (a->scheme == RBS_SCHEME_A) launch_body_plane_iso<T, 1, 0>(a);
-        else launch_body_plane_iso<T, 1, 1>(a);
+        if (a->scheme == RBS_SCHEME_A) launch_body_plane_iso<T, 1, 0>(a, w);
+        else launch_body_plane_iso<T, 1, 1>(a, w);
     }
+}
+
+int launch_body_plane_any(const rbs_body_plane_args *a, const Window &w) {
+    if (a->dtype == RBS_F64) launch_body_plane<double>(a, w);
+    else launch_body_plane<float>(a, w);
+    return check_launch("rbs_step_body_plane");
 }
 
 int validate_body_plane(const rbs_body_plane_args *a, bool need_state) {
@@ -254,6 +273,37 @@ int workspace(size_t bytes, void **out) {
         g_ws_bytes = bytes;
     }
     *out = g_ws;
+    return RBS_OK;
+}
+
+// streams / events of the pipelined host driver (created once per process) ---------------------------------
+constexpr int kMaxChunks = 8;
+struct Pipe {
+    bool ready = false;
+    int sm_count = 148;
+    cudaStream_t in = nullptr, out = nullptr, compute[2] = {nullptr, nullptr};
+    cudaEvent_t start = nullptr, finished = nullptr, arrived[kMaxChunks] = {}, stepped[kMaxChunks] = {};
+} g_pipe;
+
+int pipe_init() {
+    if (g_pipe.ready) return RBS_OK;
+    cudaError_t err = cudaSuccess;
+    int dev = 0;
+    auto ok = [&](cudaError_t e) { if (err == cudaSuccess) err = e; };
+    ok(cudaGetDevice(&dev));
+    ok(cudaDeviceGetAttribute(&g_pipe.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    ok(cudaStreamCreateWithFlags(&g_pipe.in, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&g_pipe.out, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&g_pipe.compute[0], cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&g_pipe.compute[1], cudaStreamNonBlocking));
+    ok(cudaEventCreateWithFlags(&g_pipe.start, cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&g_pipe.finished, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxChunks; ++i) {
+        ok(cudaEventCreateWithFlags(&g_pipe.arrived[i], cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&g_pipe.stepped[i], cudaEventDisableTiming));
+    }
+    if (err != cudaSuccess) return fail(RBS_ECUDA, "pipeline resources: %s", cudaGetErrorString(err));
+    g_pipe.ready = true;
     return RBS_OK;
 }
 
@@ -424,9 +474,7 @@ int rbs_step_body_plane(const rbs_body_plane_args *a) {
     int rc = validate_body_plane(a, true);
     if (rc) return rc;
     if (a->n_env == 0) return RBS_OK;
-    if (a->dtype == RBS_F64) launch_body_plane<double>(a);
-    else launch_body_plane<float>(a);
-    return check_launch("rbs_step_body_plane");
+    return launch_body_plane_any(a, whole(a));
 }
 
 int rbs_step_two_ball(const rbs_two_ball_args *a) {
@@ -480,10 +528,64 @@ int rbs_unpack_state(int dtype, long n_env, int n_body, int body_fastest, const 
     return check_launch("rbs_unpack_state");
 }
 
+// Pipelined over chunks of environments: while chunk c is being stepped, chunk c+1 is on its way in over PCIe
+// and chunk c-1 on its way out (three internal streams; the caller's stream is joined at the end).
 int rbs_run_body_plane_host(const rbs_body_plane_args *a, void *qpos_host, void *qvel_host, long total_steps) {
     int rc = validate_body_plane(a, false);
     if (rc) return rc;
-    return run_host(a, 1, 0, qpos_host, qvel_host, total_steps, rbs_step_body_plane);
+    if (total_steps < 0) return fail(RBS_EINVAL, "total_steps %ld < 0", total_steps);
+    if (a->n_env == 0) return RBS_OK;
+    if (!qpos_host || !qvel_host) return fail(RBS_EINVAL, "null host buffer");
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    const size_t es = elem_size(a->dtype);
+    const long E = a->n_env;
+    void *base = nullptr;
+    rc = workspace((size_t)E * 26 * es, &base);
+    if (rc) return rc;
+    char *qpos_d = static_cast<char *>(base), *qvel_d = qpos_d + (size_t)E * 7 * es, *state_d = qvel_d + (size_t)E * 6 * es;
+    rc = pipe_init();
+    if (rc) return rc;
+    // chunk = a whole number of full waves of CTAs, so that no chunk ends in a ragged partial wave
+    long chunk = (E + kMaxChunks - 1) / kMaxChunks;
+    const long quantum = (long)g_pipe.sm_count * 4 * rbs::kBlock;
+    chunk = ((chunk + quantum - 1) / quantum) * quantum;
+    const int n_chunks = (int)((E + chunk - 1) / chunk);
+    cudaStream_t user = as_stream(a->stream);
+    RBS_CUDA(cudaEventRecord(g_pipe.start, user));
+    RBS_CUDA(cudaStreamWaitEvent(g_pipe.in, g_pipe.start, 0));
+    for (int c = 0; c < n_chunks; ++c) {
+        const long off = c * chunk, cnt = (E - off < chunk) ? E - off : chunk;
+        RBS_CUDA(cudaMemcpyAsync(qpos_d + off * 7 * es, (char *)qpos_host + off * 7 * es, cnt * 7 * es, cudaMemcpyHostToDevice, g_pipe.in));
+        RBS_CUDA(cudaMemcpyAsync(qvel_d + off * 6 * es, (char *)qvel_host + off * 6 * es, cnt * 6 * es, cudaMemcpyHostToDevice, g_pipe.in));
+        RBS_CUDA(cudaEventRecord(g_pipe.arrived[c], g_pipe.in));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        const long off = c * chunk, cnt = (E - off < chunk) ? E - off : chunk;
+        cudaStream_t cs = g_pipe.compute[c & 1];
+        char *state_c = state_d + off * 13 * es;
+        RBS_CUDA(cudaStreamWaitEvent(cs, g_pipe.arrived[c], 0));
+        rc = rbs_pack_state(a->dtype, cnt, 1, 0, qpos_d + off * 7 * es, qvel_d + off * 6 * es, state_c, cnt, cs);
+        if (rc) return rc;
+        rbs_body_plane_args local = *a;
+        const Window w{off, cnt, state_c, cnt, cs};
+        for (long done = 0; done < total_steps;) {
+            const long k = total_steps - done < a->substeps ? total_steps - done : a->substeps;
+            local.substeps = (int)k;
+            rc = launch_body_plane_any(&local, w);
+            if (rc) return rc;
+            done += k;
+        }
+        rc = rbs_unpack_state(a->dtype, cnt, 1, 0, state_c, cnt, qpos_d + off * 7 * es, qvel_d + off * 6 * es, cs);
+        if (rc) return rc;
+        RBS_CUDA(cudaEventRecord(g_pipe.stepped[c], cs));
+        RBS_CUDA(cudaStreamWaitEvent(g_pipe.out, g_pipe.stepped[c], 0));
+        RBS_CUDA(cudaMemcpyAsync((char *)qpos_host + off * 7 * es, qpos_d + off * 7 * es, cnt * 7 * es, cudaMemcpyDeviceToHost, g_pipe.out));
+        RBS_CUDA(cudaMemcpyAsync((char *)qvel_host + off * 6 * es, qvel_d + off * 6 * es, cnt * 6 * es, cudaMemcpyDeviceToHost, g_pipe.out));
+    }
+    RBS_CUDA(cudaEventRecord(g_pipe.finished, g_pipe.out));
+    RBS_CUDA(cudaStreamWaitEvent(user, g_pipe.finished, 0));
+    RBS_CUDA(cudaStreamSynchronize(user));
+    return RBS_OK;
 }
 
 int rbs_run_two_ball_host(const rbs_two_ball_args *a, void *qpos_host, void *qvel_host, long total_steps) {

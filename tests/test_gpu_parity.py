@@ -461,6 +461,22 @@ def test_host_buffer_driver_matches_device_path(rb):
     assert (qp_h.numpy() == gq).all() and (qv_h.numpy() == gv).all()
 
 
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_host_buffer_driver_pipelined_chunks(rb, arith):
+    """Several pipeline chunks (ragged last one), per-env parameters, a step count that is not a multiple of the
+    fuse factor: the host-buffer call returns exactly what the device-resident path computes."""
+    from rigidbody_simulation_b200 import stepper, synth
+    E = 400_003
+    s = synth.sphere_incline(E)
+    model, data = make_single(rb, "sphere", [0.2], 0.7, s["qpos"], s["qvel"])
+    model.set_per_env(restitution=s["restitution"], friction=s["friction"])
+    stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=75, arith=arith)
+    qp_h, qv_h = s["qpos"].copy(), s["qvel"].copy()            # pageable NumPy buffers work too
+    stepper.run_body_plane_host(model, qp_h, qv_h, 75, dt=s["dt"], restitution=None, friction_coeff=None, substeps=32, arith=arith)
+    gq, gv = state_of(data)
+    assert (qp_h == gq).all() and (qv_h == gv).all()
+
+
 def test_pack_unpack_roundtrip_and_empty(rb):
     import ctypes
     lib = rb._lib.load()
