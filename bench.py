@@ -274,6 +274,10 @@ def b200_arm(args):
     fused_gbs = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     k1_gbs = bytes_per_launch / (k1_launch_ms * 1e-3) / 1e9
 
+    # --- optional end-of-run gather of logged statistics: the only collective in the whole job -------------------
+    stats = shard.gather_stats(shard.local_stats(data, float(model.body_mass[-1]), float(model.opt.gravity[2])),
+                               env_substeps=E * S * args.steps)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -291,12 +295,17 @@ def b200_arm(args):
                                         "CUDA-core peak)",
                          "flops_per_env_substep": flops_per_substep, "contacts_per_env_substep": c_per,
                          "impulses_per_env_substep": i_per, "launch_ms": launch_ms, "substeps_per_launch": F,
-                         "hbm_GBps_of_same_launch": fused_gbs, "traffic": None},
+                         "hbm_GBps_of_same_launch": fused_gbs,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture
+                         # summarised in profiles/r1_summary.md (valid for the default 1,048,576-env fp64 shape only)
+                         "traffic": 176.1e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
             "roofline_k1": {"bound": "hbm", "kernel": "same kernel, 1 substep per launch (the reference's per-frame call)",
                             "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
                             "peak_source": hbm_src, "bytes_per_env": (26 + 2) * esize, "launch_ms": k1_launch_ms,
-                            "env_steps_per_s": world * E / (k1_launch_ms * 1e-3), "traffic": None},
+                            "env_steps_per_s": world * E / (k1_launch_ms * 1e-3),
+                            "traffic": 177.6e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
         }
+        line["end_of_run_stats"] = stats
         line["other_policy"] = {"arith": other, "value": other_value, "unit": METRIC,
                                 "note": "strict = the reference's rounding sequence, bit-for-bit the C oracle on "
                                         "inertia-free paths; fast = FMA / reciprocal-multiply re-association, <= 1e-12 "

@@ -1,5 +1,8 @@
+"""Divergence of the fast-policy GPU trajectory from the CPU oracle as a function of step count (config 2,\n200,000 envs, fp64) plus per-env contact-event count mismatches.  Output transcribed in r1_summary.md."""
 import sys, os, numpy as np, torch
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/oracle'); sys.path.insert(0, '/root/repo/tests')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
+    sys.path.insert(0, p)
 import c_oracle as co
 from helpers import comp_rel_err
 import rigidbody_simulation_b200 as rb

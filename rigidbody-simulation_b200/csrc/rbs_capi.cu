@@ -248,10 +248,18 @@ template <typename T> void launch_multi_sphere(const rbs_multi_sphere_args *a) {
     const rbs::MultiSphereParams<T> p = make_params<T>(a, epb);
     const unsigned grid = (unsigned)((a->n_env + epb - 1) / epb);
     const size_t smem = (size_t)epb * B * 4 * sizeof(T);
-    if (a->inertia_mode == RBS_INERTIA_ISOTROPIC)
-        rbs::step_multi_sphere_kernel<T, 1><<<grid, threads, smem, as_stream(a->stream)>>>(p);
-    else
-        rbs::step_multi_sphere_kernel<T, 0><<<grid, threads, smem, as_stream(a->stream)>>>(p);
+    cudaStream_t st = as_stream(a->stream);
+    const bool iso = a->inertia_mode == RBS_INERTIA_ISOTROPIC;
+    if (threads <= 256) {
+        if (iso) rbs::step_multi_sphere_kernel<T, 1, 256><<<grid, threads, smem, st>>>(p);
+        else rbs::step_multi_sphere_kernel<T, 0, 256><<<grid, threads, smem, st>>>(p);
+    } else if (threads <= 512) {
+        if (iso) rbs::step_multi_sphere_kernel<T, 1, 512><<<grid, threads, smem, st>>>(p);
+        else rbs::step_multi_sphere_kernel<T, 0, 512><<<grid, threads, smem, st>>>(p);
+    } else {
+        if (iso) rbs::step_multi_sphere_kernel<T, 1, 1024><<<grid, threads, smem, st>>>(p);
+        else rbs::step_multi_sphere_kernel<T, 0, 1024><<<grid, threads, smem, st>>>(p);
+    }
 }
 
 // cached device workspace of the host-buffer drivers -------------------------------------------

@@ -514,3 +514,106 @@ def test_error_behaviour(rb):
     assert lib.rbs_step_body_plane(ctypes.byref(a)) == rb._lib.RBS_EINVAL and b"stride" in lib.rbs_last_error()
     with pytest.raises(ValueError):
         rb.compute_collision_impulse_friction(1.0, None, np.zeros(4), np.zeros(3), np.zeros(3), np.zeros(3), 1.0, 0.5)
+
+
+# ------------------------------------------------------------------------------------ streams, graphs, edge cases
+def test_cuda_graph_capture_and_side_stream(rb):
+    """Every entry point only enqueues on the caller's stream, so a loop of one-substep launches (the reference's
+    per-frame call) can be captured in a CUDA graph and replayed; results equal the eager launches."""
+    from rigidbody_simulation_b200 import stepper, synth
+    E = 50_000
+    s = synth.sphere_incline(E)
+
+    def fresh():
+        model, data = make_single(rb, "sphere", [0.2], 0.7, s["qpos"], s["qvel"])
+        model.set_per_env(restitution=s["restitution"], friction=s["friction"])
+        return model, data
+
+    model, data = fresh()
+    for _ in range(48):
+        stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=1)
+    eager = data.state.clone()
+
+    model, data = fresh()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=1)     # warm-up outside capture
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(16):
+                stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=1)
+        data.set_state(s["qpos"], s["qvel"])
+        data.n_contacts.zero_()
+        data.n_impulses.zero_()
+        for _ in range(3):
+            graph.replay()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    assert torch.equal(data.state, eager)
+
+
+def test_nan_and_degenerate_inputs_propagate_like_the_reference(rb):
+    """The reference filters only isnan(dist) (collision.py:74): a NaN env stays NaN and does not disturb its
+    neighbours; a sphere exactly touching (dist == 0) is not a contact (dist < 0 is required)."""
+    from rigidbody_simulation_b200 import stepper
+    E = 256
+    qpos = np.tile(np.array([0, 0, 1.0, 1, 0, 0, 0.0]), (E, 1))
+    qvel = np.zeros((E, 6))
+    qpos[7, 2] = np.nan
+    qpos[9, 2] = 0.2                      # exactly touching the flat plane, at rest
+    model, data = make_single(rb, "sphere", [0.2], 0.0, qpos, qvel)
+    stepper.step_body_plane(model, data, -1, 0.009, 1.0, 0.5, 0.0, substeps=1)
+    qp, qv = state_of(data)
+    assert np.isnan(qp[7, 2]) and np.isfinite(np.delete(qp, 7, axis=0)).all()
+    calls, _ = data.counters()
+    assert calls.sum() == 0               # nobody is in contact on the first step, including env 9
+    ref_p, ref_v = qpos[:1].copy(), qvel[:1].copy()
+    co.step_body_plane(ref_p, ref_v, 1, geom="sphere", mass=model.body_mass[-1], inertia=model.body_inertia[-1], size=0.2,
+                       plane_pos=[0, 0, 0], plane_normal=[0, 0, 1], gravity=G, dt=0.009, restitution=1.0, friction=0.5, threshold=0.0)
+    assert (qp[0] == ref_p[0]).all() and (qv[0] == ref_v[0]).all()
+
+
+def test_multi_sphere_ragged_and_maximum_body_counts(rb):
+    """B that does not divide the CTA (ragged lanes), B = 1 (no partner) and the ABI maximum B = 1024."""
+    from rigidbody_simulation_b200 import stepper, synth
+    from rigidbody_simulation_b200.src.simulation import multi_sphere_bounce as ms
+    for B, E, steps in ((1, 300, 40), (3, 1001, 40), (100, 37, 25), (1024, 2, 3)):
+        s = synth.multi_sphere(E, n_body=B, friction=0.2)
+        model, data = ms.build(E, n_body=B)
+        data.set_state(s["qpos"], s["qvel"])
+        qp = s["qpos"].reshape(E, B, 7).copy()
+        qv = s["qvel"].reshape(E, B, 6).copy()
+        cnt = (np.zeros((E, B), np.uint32), np.zeros((E, B), np.uint32))
+        co.step_multi_sphere(qp, qv, steps, mass=model.body_mass[1], inertia=model.body_inertia[1], radius=0.1,
+                             plane_pos=[0, 0, 0], plane_normal=[0, 0, 1], gravity=G, dt=0.01, restitution=1.0, friction=0.2, counters=cnt)
+        stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.2, substeps=steps)
+        gq, gv = state_of(data)
+        assert comp_rel_err(gq.ravel(), qp.ravel(), 1e-3) <= 1e-9, B
+        calls, imps = data.counters()
+        assert (calls == cnt[0]).all() and (imps == cnt[1]).all(), B
+
+
+def test_padded_stride_and_applied_wrench_per_env(rb):
+    """stride > n_env (a window into a larger allocation) and a per-env applied wrench through the raw C ABI."""
+    import ctypes
+    from rigidbody_simulation_b200 import stepper, synth
+    E, pad = 5000, 5120
+    s = synth.sphere_incline(E)
+    model, data = make_single(rb, "sphere", [0.2], 0.7, s["qpos"], s["qvel"])
+    rng = np.random.default_rng(3)
+    xf = np.concatenate([rng.uniform(-2, 2, (E, 3)), rng.uniform(-0.05, 0.05, (E, 3))], axis=1)
+    data.set_xfrc(xf)
+    big = torch.full((13, pad), float("nan"), dtype=torch.float64, device="cuda")
+    big[:, :E] = data.state[:, 0, :]
+    a = stepper.body_plane_args(model, data, -1, s["dt"], 0.8, 0.4, 0.0, rb._lib.RBS_SCHEME_A, 20)
+    a.state, a.stride = ctypes.c_void_p(big.data_ptr()), pad
+    a.stream = stepper.current_stream(model.device)
+    rb._lib.check(rb._lib.load().rbs_step_body_plane(ctypes.byref(a)))
+    qp, qv = s["qpos"].copy(), s["qvel"].copy()
+    co.step_body_plane(qp, qv, 20, geom="sphere", mass=model.body_mass[-1], inertia=model.body_inertia[-1], size=0.2,
+                       plane_pos=[0, 0, 0], plane_normal=model.plane_normal, gravity=G, dt=s["dt"], restitution=0.8,
+                       friction=0.4, threshold=0.0, xfrc=xf)
+    got = big[:, :E].cpu().numpy()
+    assert np.isnan(big[:, E:].cpu().numpy()).all()                       # the padding is never touched
+    assert comp_rel_err(got[:7].T, qp, 1e-3) <= 1e-11 and comp_rel_err(got[7:].T, qv, 1e-3) <= 1e-11

@@ -196,3 +196,12 @@ def test_batched_data_views_on_cpu():
         assert (q[0] == m.qpos0).all() and (q[1] == qp[1]).all() and (d.qvel.torch().numpy()[3] == 0).all()
         d.reset()
         assert (d.qpos.torch().numpy() == m.qpos0).all()
+
+
+def test_cli_help_and_headless_flags():
+    code = ("import sys; sys.path.insert(0, 'rigidbody-simulation_b200');"
+            "from src.simulate import main; main(['--help'])")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0
+    for flag in ("--sim", "--headless", "--steps", "--envs", "--dtype", "--substeps-per-launch", "--seed", "--gpus"):
+        assert flag in r.stdout
