@@ -1,4 +1,5 @@
-"""Divergence of the fast-policy GPU trajectory from the CPU oracle as a function of step count (config 2,\n200,000 envs, fp64) plus per-env contact-event count mismatches.  Output transcribed in r1_summary.md."""
+"""Divergence of the fast-policy GPU trajectory from the CPU oracle as a function of step count (config 2,
+200,000 envs, fp64) plus per-env contact-event count mismatches.  Output transcribed in r1_summary.md."""
 import sys, os, numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
