@@ -110,7 +110,7 @@ typedef struct rbs_body_plane_args {
     int substeps;              /* >= 1 */
     int arith;                 /* RBS_ARITH_STRICT: the reference's rounding sequence (bit-faithful);
                                   RBS_ARITH_FAST: FMA / reciprocal-multiply re-association, <= 1e-12 per step in
-                                  fp64; implemented for sphere + scheme A + isotropic inertia */
+                                  fp64; implemented for scheme A + isotropic inertia (sphere or box) */
     void *state;               /* [13][stride], env-major, n_body = 1 */
     const void *mass;          double mass_u;
     const void *inertia;       double inertia_u[3];   /* [3][n_env] body-frame principal moments */
@@ -157,6 +157,8 @@ typedef struct rbs_multi_sphere_args {
     int substeps;
     int n_body;                /* 1 .. 1024 */
     int inertia_mode;
+    int arith;                 /* RBS_ARITH_FAST needs RBS_INERTIA_ISOTROPIC (spheres: always valid) */
+    int reserved;
     long n_env;
     long stride;               /* >= n_env * n_body */
     void *state;               /* [13][stride], body-fastest */

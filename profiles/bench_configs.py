@@ -58,9 +58,10 @@ for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
         model = scenes.cube_on_plane(E, theta=s["theta"], device=dev, dtype=dtype)
         data = rb.BatchedData(model)
         data.set_state(s["qpos"], s["qvel"])
-        for K in (1, 64):
-            f = lambda: stepper.step_body_plane(model, data, -1, s["dt"], 0.2, 0.6, 1e-4, substeps=K, count=False)
-            report(f"cfg4 cube_{kind} {tag} strict", E, 1, K, timed(f))
+        for arith in ("strict", "fast"):
+            for K in (1, 64):
+                f = lambda: stepper.step_body_plane(model, data, -1, s["dt"], 0.2, 0.6, 1e-4, substeps=K, count=False, arith=arith)
+                report(f"cfg4 cube_{kind} {tag} {arith}", E, 1, K, timed(f))
     # config 3 two balls ---------------------------------------------------------------------------------------
     s = synth.two_ball(E)
     model, data = ball_collision.build(E, device=dev, dtype=dtype)
@@ -73,6 +74,7 @@ for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
         s = synth.multi_sphere(E5, n_body=64, friction=0.0)
         model, data = multi_sphere_bounce.build(E5, device=dev, dtype=dtype, n_body=64)
         data.set_state(s["qpos"], s["qvel"])
-        for K in (1, 16):
-            f = lambda: stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.0, substeps=K, count=False)
-            report(f"cfg5 multi_sphere64 {tag} strict", E5, 64, K, timed(f, reps=3, warm=1))
+        for arith in ("strict", "fast"):
+            for K in (1, 16):
+                f = lambda: stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.0, substeps=K, count=False, arith=arith)
+                report(f"cfg5 multi_sphere64 {tag} {arith}", E5, 64, K, timed(f, reps=3, warm=1))

@@ -125,8 +125,14 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
     }
 }
 
+template <typename T> void launch_box_plane_fast(const rbs_body_plane_args *a, const Window &w) {
+    const rbs::BodyPlaneParams<T> p = make_params<T>(a, w);
+    rbs::step_box_plane_fast_kernel<T, 4><<<blocks_for(w.cnt, rbs::kBlock), rbs::kBlock, 0, w.stream>>>(p);
+}
+
 template <typename T> void launch_body_plane(const rbs_body_plane_args *a, const Window &w) {
-    if (a->arith == RBS_ARITH_FAST) return launch_sphere_plane_fast<T>(a, w);
+    if (a->arith == RBS_ARITH_FAST)
+        return a->geom == RBS_GEOM_SPHERE ? launch_sphere_plane_fast<T>(a, w) : launch_box_plane_fast<T>(a, w);
     if (a->geom == RBS_GEOM_SPHERE) {
         if (a->scheme == RBS_SCHEME_A) launch_body_plane_iso<T, 0, 0>(a, w);
         else launch_body_plane_iso<T, 0, 1>(a, w);
@@ -150,9 +156,8 @@ int validate_body_plane(const rbs_body_plane_args *a, bool need_state) {
     if (a->inertia_mode != RBS_INERTIA_GENERAL && a->inertia_mode != RBS_INERTIA_ISOTROPIC)
         return fail(RBS_EINVAL, "rbs_step_body_plane: bad inertia_mode %d", a->inertia_mode);
     if (a->arith != RBS_ARITH_STRICT && a->arith != RBS_ARITH_FAST) return fail(RBS_EINVAL, "rbs_step_body_plane: bad arith %d", a->arith);
-    if (a->arith == RBS_ARITH_FAST &&
-        !(a->geom == RBS_GEOM_SPHERE && a->scheme == RBS_SCHEME_A && a->inertia_mode == RBS_INERTIA_ISOTROPIC))
-        return fail(RBS_EINVAL, "rbs_step_body_plane: RBS_ARITH_FAST is implemented for sphere + scheme A + isotropic inertia only");
+    if (a->arith == RBS_ARITH_FAST && !(a->scheme == RBS_SCHEME_A && a->inertia_mode == RBS_INERTIA_ISOTROPIC))
+        return fail(RBS_EINVAL, "rbs_step_body_plane: RBS_ARITH_FAST is implemented for scheme A + isotropic inertia only");
     if (a->n_env < 0) return fail(RBS_EINVAL, "rbs_step_body_plane: n_env %ld < 0", a->n_env);
     if (a->substeps < 1) return fail(RBS_EINVAL, "rbs_step_body_plane: substeps %d < 1", a->substeps);
     if (need_state) {
@@ -232,6 +237,9 @@ int validate_multi_sphere(const rbs_multi_sphere_args *a, bool need_state) {
     if (a->substeps < 1) return fail(RBS_EINVAL, "rbs_step_multi_sphere: substeps %d < 1", a->substeps);
     if (a->inertia_mode != RBS_INERTIA_GENERAL && a->inertia_mode != RBS_INERTIA_ISOTROPIC)
         return fail(RBS_EINVAL, "rbs_step_multi_sphere: bad inertia_mode %d", a->inertia_mode);
+    if (a->arith != RBS_ARITH_STRICT && a->arith != RBS_ARITH_FAST) return fail(RBS_EINVAL, "rbs_step_multi_sphere: bad arith %d", a->arith);
+    if (a->arith == RBS_ARITH_FAST && a->inertia_mode != RBS_INERTIA_ISOTROPIC)
+        return fail(RBS_EINVAL, "rbs_step_multi_sphere: RBS_ARITH_FAST needs RBS_INERTIA_ISOTROPIC");
     if (need_state) {
         if (a->n_env > 0 && !a->state) return fail(RBS_EINVAL, "rbs_step_multi_sphere: null state");
         if (a->stride < a->n_env * a->n_body)
@@ -250,6 +258,12 @@ template <typename T> void launch_multi_sphere(const rbs_multi_sphere_args *a) {
     const size_t smem = (size_t)epb * B * 4 * sizeof(T);
     cudaStream_t st = as_stream(a->stream);
     const bool iso = a->inertia_mode == RBS_INERTIA_ISOTROPIC;
+    if (a->arith == RBS_ARITH_FAST) {
+        if (threads <= 256) rbs::step_multi_sphere_fast_kernel<T, 256><<<grid, threads, smem, st>>>(p);
+        else if (threads <= 512) rbs::step_multi_sphere_fast_kernel<T, 512><<<grid, threads, smem, st>>>(p);
+        else rbs::step_multi_sphere_fast_kernel<T, 1024><<<grid, threads, smem, st>>>(p);
+        return;
+    }
     if (threads <= 256) {
         if (iso) rbs::step_multi_sphere_kernel<T, 1, 256><<<grid, threads, smem, st>>>(p);
         else rbs::step_multi_sphere_kernel<T, 0, 256><<<grid, threads, smem, st>>>(p);

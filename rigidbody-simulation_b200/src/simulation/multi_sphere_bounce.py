@@ -33,12 +33,12 @@ def build(nenv=1, device=None, dtype=torch.float64, n_body=None):
 
 
 def custom_step_multi_sphere(model, data, dt=timestep, restitution=restitution_coefficient, substeps=1,
-                             friction=None):
+                             friction=None, arith="strict"):
     """Per ball: gravity, impulses for every start-of-step contact touching the ball, pose integration (:42-92).
     Returns None like the reference (:92)."""
     mj.mj_forward(model, data)                               # :43
     stepper.step_multi_sphere(model, data, dt, restitution, friction_coefficient if friction is None else friction,
-                              substeps=substeps)
+                              substeps=substeps, arith=arith)
     return None
 
 

@@ -138,7 +138,7 @@ def step_two_ball(model, data, dt, restitution, friction, radius=0.1, substeps=1
     _lib.check(_lib.load().rbs_step_two_ball(ctypes.byref(a)))
 
 
-def multi_sphere_args(model, data, dt, restitution, friction, substeps, count=True, strict_inertia=False):
+def multi_sphere_args(model, data, dt, restitution, friction, substeps, count=True, strict_inertia=False, arith="strict"):
     _require_cuda(model)
     if data.layout != "body":
         raise ValueError("the multi-sphere step needs BatchedData(model, layout='body')")
@@ -169,6 +169,7 @@ def multi_sphere_args(model, data, dt, restitution, friction, substeps, count=Tr
     a.inertia_u = _lib.D3(*[float(v) for v in model.body_inertia[first]])
     a.radius, a.radius_u = _ptr(pe.get("radius")), float(geoms[0].size[0])
     a.inertia_mode = RBS_INERTIA_GENERAL if strict_inertia else RBS_INERTIA_ISOTROPIC   # spheres: I1 = I2 = I3
+    a.arith = ARITH[arith]
     a.plane_point = _lib.D3(*model.plane_point)
     a.plane_normal = _lib.D3(*model.plane_normal)
     a.gravity = _lib.D3(*[float(g) for g in model.opt.gravity])
@@ -178,8 +179,8 @@ def multi_sphere_args(model, data, dt, restitution, friction, substeps, count=Tr
     return a
 
 
-def step_multi_sphere(model, data, dt, restitution, friction, substeps=1, count=True, strict_inertia=False):
-    a = multi_sphere_args(model, data, dt, restitution, friction, substeps, count, strict_inertia)
+def step_multi_sphere(model, data, dt, restitution, friction, substeps=1, count=True, strict_inertia=False, arith="strict"):
+    a = multi_sphere_args(model, data, dt, restitution, friction, substeps, count, strict_inertia, arith)
     a.stream = current_stream(model.device)
     _lib.check(_lib.load().rbs_step_multi_sphere(ctypes.byref(a)))
 

@@ -290,22 +290,43 @@ def test_fast_policy_golden_and_scope(rb, golden):
     calls, imps = data.counters()
     assert (int(calls.sum()), int(imps.sum())) == (131, 125)
     assert np.max(np.abs(np.asarray(data.qpos) - s["qpos"])) < 1e-9
-    # the policy exists for the headline kernel only; anything else is refused, not silently strict
+    # the policy exists for scheme A + isotropic inertia; anything else is refused, not silently strict
     c = golden("cube_random")["bounce"]
     model, data = make_single(rb, "box", c["half"], 0.0, col(c["envs"], "qpos0"), col(c["envs"], "qvel0"))
     with pytest.raises(ValueError):
+        stepper.step_body_plane(model, data, -1, 0.009, 0.2, 0.6, 1e-4, arith="fast", scheme=rb._lib.RBS_SCHEME_GENERAL)
+    with pytest.raises(ValueError):
+        stepper.step_body_plane(model, data, -1, 0.009, 0.2, 0.6, 1e-4, arith="fast", strict_inertia=True)
+    model, data = make_single(rb, "box", [0.3, 0.2, 0.1], 0.0, col(c["envs"], "qpos0"), col(c["envs"], "qvel0"))
+    with pytest.raises(ValueError):                       # anisotropic box
         stepper.step_body_plane(model, data, -1, 0.009, 0.2, 0.6, 1e-4, arith="fast")
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, F64_STEP), (np.float32, F32_STEP)])
 @pytest.mark.parametrize("kind", ["bounce", "incline"])
-def test_cube_50k_vs_oracle(rb, dtype, tol, kind):
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_cube_50k_vs_oracle(rb, dtype, tol, kind, arith):
     from rigidbody_simulation_b200 import synth
-    out, counts_ok, ncalls = _oracle_vs_gpu_single(rb, "box", lambda E: synth.cube(E, kind=kind), 50_000, 120, dtype, False)
+    out, counts_ok, ncalls = _oracle_vs_gpu_single(rb, "box", lambda E: synth.cube(E, kind=kind), 50_000, 120, dtype, False,
+                                                   arith=arith)
     assert out[1][0] <= tol, out
     assert ncalls > 50_000
     if dtype == np.float64:
-        assert counts_ok and out[120][0] <= 1e-8, out
+        assert counts_ok and out[120][0] <= (1e-8 if arith == "strict" else 1e-6), out
+
+
+def test_cube_golden_fast_policy(rb, golden):
+    from rigidbody_simulation_b200.src.physics.time_integeration import timestep_integration as step
+    g = golden("cube_random")
+    for kind in ("bounce", "incline"):
+        c = g[kind]
+        envs = c["envs"]
+        model, data = make_single(rb, "box", c["half"], c["theta"], col(envs, "qpos0"), col(envs, "qvel0"))
+        devs = _step_snapshots(model, data, c, envs, step, restitution=c["e"], friction_coeff=c["mu"], arith="fast")
+        assert devs[1] <= F64_STEP, (kind, devs)
+        assert devs[c["steps"]] <= 1e-5, (kind, devs)
+        calls, imps = data.counters()
+        assert (calls[:, 0] == col(envs, "calls")).all() and (imps[:, 0] == col(envs, "impulses")).all()
 
 
 # ------------------------------------------------------------------------------------ two balls
@@ -381,9 +402,10 @@ def test_multi_sphere_golden(rb, golden):
         assert calls[0].tolist() == case["calls"] and imps[0].tolist() == case["impulses"]
 
 
+@pytest.mark.parametrize("arith", ["strict", "fast"])
 @pytest.mark.parametrize("dtype,tol", [(np.float64, F64_STEP), (np.float32, F32_STEP)])
 @pytest.mark.parametrize("B", [64, 27, 5])
-def test_multi_sphere_vs_oracle(rb, dtype, tol, B):
+def test_multi_sphere_vs_oracle(rb, dtype, tol, B, arith):
     from rigidbody_simulation_b200 import stepper, synth
     from rigidbody_simulation_b200.src.simulation import multi_sphere_bounce as ms
     E = 1500 if B == 64 else 4000
@@ -398,12 +420,17 @@ def test_multi_sphere_vs_oracle(rb, dtype, tol, B):
     done = 0
     for upto in (1, 10, 60):
         co.step_multi_sphere(qp, qv, upto - done, **okw)
-        stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.3, substeps=upto - done)
+        stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.3, substeps=upto - done, arith=arith)
         done = upto
         gq, gv = state_of(data)
-        err = max(comp_rel_err(gq.ravel(), qp.ravel(), 1e-3), comp_rel_err(gv.ravel(), qv.ravel(), 1e-3))
-        if upto <= 10:
-            assert err <= (tol if upto == 1 else tol * 10), (upto, err)
+        # components that cancel to ~0 carry the absolute rounding error of O(1) intermediates; in fp32 under the
+        # re-associated policy the relative measure therefore uses a floor of 1e-2 (positions/velocities are O(1))
+        floor = 1e-2 if (dtype == np.float32 and arith == "fast") else 1e-3
+        err = max(comp_rel_err(gq.ravel(), qp.ravel(), floor), comp_rel_err(gv.ravel(), qv.ravel(), floor))
+        if upto == 1:
+            assert err <= tol, (upto, err)
+        elif upto == 10:        # collisions amplify rounding differences: 10x per decade for strict, more for fast
+            assert err <= tol * (10 if arith == "strict" else 1000), (upto, err)
     if dtype == np.float64:
         calls, imps = data.counters()
         mismatch = (calls != cnt[0]).any(axis=1) | (imps != cnt[1]).any(axis=1)
