@@ -224,16 +224,20 @@ def b200_arm(args):
     c_per = float(data.n_contacts.sum().item()) / (E * F)
     i_per = float(data.n_impulses.sum().item()) / (E * F)
 
-    # --- the other arithmetic policy, same job, continuing from the same (steady-state) regime ------------------
-    other = "strict" if args.arith == "fast" else "fast"
+    # --- the strict arithmetic policy (both inertia variants), same job, continuing from the same regime ---------
+    others = {}
+    for label, kw in (("strict", dict(arith="strict")), ("strict_isotropic_shortcut", dict(arith="strict", strict_inertia=False))):
+        if args.arith == "strict" and label == "strict":
+            kw = dict(arith="fast")
+            label = "fast"
 
-    def other_step():
-        for _ in range(S // F):
-            stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=F, count=False, arith=other)
+        def other_step(kw=kw):
+            for _ in range(S // F):
+                stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=F, count=False, **kw)
 
-    n_other = max(2, args.steps // 2)
-    other_ms, _, _ = timed(other_step, n_other, 1)
-    other_value = world * E * S / (other_ms / n_other * 1e-3)
+        n_other = max(2, args.steps // 3)
+        other_ms, _, _ = timed(other_step, n_other, 1)
+        others[label] = world * E * S / (other_ms / n_other * 1e-3)
 
     # --- K=1 streaming regime (HBM-bound): one launch per substep ---------------------------------------
     k1_launches = args.k1_launches
@@ -306,10 +310,11 @@ def b200_arm(args):
                             "traffic": 177.6e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
         }
         line["end_of_run_stats"] = stats
-        line["other_policy"] = {"arith": other, "value": other_value, "unit": METRIC,
-                                "note": "strict = the reference's rounding sequence, bit-for-bit the C oracle on "
-                                        "inertia-free paths; fast = FMA / reciprocal-multiply re-association, <= 1e-12 "
-                                        "relative per step and exact contact-event counts (tests/test_gpu_parity.py)"}
+        line["other_policies"] = {
+            "values": others, "unit": METRIC,
+            "note": "strict = the reference's rounding sequence with the literal inv(R diag(I) R^T): bit-for-bit the C oracle "
+                    "(profiles/r1_parity_report.md); strict_isotropic_shortcut = same but inv = (1/I)*Id for I1=I2=I3; fast = "
+                    "FMA / reciprocal-multiply re-association, <= 1e-12 relative per step (tests/test_gpu_parity.py)"}
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline_native"] = cpu_native

@@ -51,7 +51,7 @@ ARITH = {"strict": _lib.RBS_ARITH_STRICT, "fast": _lib.RBS_ARITH_FAST}
 
 
 def body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold, scheme, substeps,
-                    count=True, strict_inertia=False, arith="strict"):
+                    count=True, strict_inertia=None, arith="strict"):
     """rbs_body_plane_args for the single free body ``body_id`` of ``model`` resting on its plane."""
     _require_cuda(model)
     if model.nfree != 1 or data.layout != "env":
@@ -83,6 +83,10 @@ def body_plane_args(model, data, body_id, dt, restitution, friction_coeff, conta
     size_t = pe.get("size")
     a.size = _ptr(size_t)
     a.size_u = _lib.D3(*[float(v) for v in geom.size])
+    # strict policy: literal inv(R diag(I) R^T) by default (bit-for-bit the oracle); strict_inertia=False opts into the
+    # isotropic shortcut (1/I)*Id, which is a few ulp away.  The fast policy always uses the shortcut.
+    if strict_inertia is None:
+        strict_inertia = arith == "strict"
     iso = inertia_t is None and _isotropic(model.body_inertia[bid]) and not strict_inertia
     a.inertia_mode = RBS_INERTIA_ISOTROPIC if iso else RBS_INERTIA_GENERAL
     # None = "use the per-environment values attached to the model" (randomised configs)
@@ -104,7 +108,7 @@ def body_plane_args(model, data, body_id, dt, restitution, friction_coeff, conta
 
 
 def step_body_plane(model, data, body_id, dt, restitution, friction_coeff, contact_threshold,
-                    scheme=RBS_SCHEME_A, substeps=1, count=True, strict_inertia=False, arith="strict"):
+                    scheme=RBS_SCHEME_A, substeps=1, count=True, strict_inertia=None, arith="strict"):
     """arith: "strict" reproduces the reference's rounding sequence; "fast" re-associates for the FP pipe
     (sphere + scheme A + isotropic inertia only; <= 1e-12 relative per step in fp64)."""
     a = body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold, scheme, substeps,
@@ -138,7 +142,7 @@ def step_two_ball(model, data, dt, restitution, friction, radius=0.1, substeps=1
     _lib.check(_lib.load().rbs_step_two_ball(ctypes.byref(a)))
 
 
-def multi_sphere_args(model, data, dt, restitution, friction, substeps, count=True, strict_inertia=False, arith="strict"):
+def multi_sphere_args(model, data, dt, restitution, friction, substeps, count=True, strict_inertia=None, arith="strict"):
     _require_cuda(model)
     if data.layout != "body":
         raise ValueError("the multi-sphere step needs BatchedData(model, layout='body')")
@@ -168,6 +172,8 @@ def multi_sphere_args(model, data, dt, restitution, friction, substeps, count=Tr
     a.inertia = _ptr(pe.get("inertia"))
     a.inertia_u = _lib.D3(*[float(v) for v in model.body_inertia[first]])
     a.radius, a.radius_u = _ptr(pe.get("radius")), float(geoms[0].size[0])
+    if strict_inertia is None:
+        strict_inertia = arith == "strict"
     a.inertia_mode = RBS_INERTIA_GENERAL if strict_inertia else RBS_INERTIA_ISOTROPIC   # spheres: I1 = I2 = I3
     a.arith = ARITH[arith]
     a.plane_point = _lib.D3(*model.plane_point)
@@ -179,7 +185,7 @@ def multi_sphere_args(model, data, dt, restitution, friction, substeps, count=Tr
     return a
 
 
-def step_multi_sphere(model, data, dt, restitution, friction, substeps=1, count=True, strict_inertia=False, arith="strict"):
+def step_multi_sphere(model, data, dt, restitution, friction, substeps=1, count=True, strict_inertia=None, arith="strict"):
     a = multi_sphere_args(model, data, dt, restitution, friction, substeps, count, strict_inertia, arith)
     a.stream = current_stream(model.device)
     _lib.check(_lib.load().rbs_step_multi_sphere(ctypes.byref(a)))
@@ -200,7 +206,7 @@ def _host_ptr(arr, dtype, shape):
 
 
 def run_body_plane_host(model, qpos, qvel, total_steps, body_id=-1, dt=None, restitution=1.0, friction_coeff=1.0,
-                        contact_threshold=0.0, scheme=RBS_SCHEME_A, substeps=32, strict_inertia=False, arith="strict"):
+                        contact_threshold=0.0, scheme=RBS_SCHEME_A, substeps=32, strict_inertia=None, arith="strict"):
     """Advance host arrays qpos[E,7], qvel[E,6] (in place) by ``total_steps`` steps of A5/A6/A7.
     H2D, the launches and D2H all happen inside; returns after the stream is synchronised."""
     data = _HostShim(model, 1)

@@ -205,3 +205,17 @@ def test_cli_help_and_headless_flags():
     assert r.returncode == 0
     for flag in ("--sim", "--headless", "--steps", "--envs", "--dtype", "--substeps-per-launch", "--seed", "--gpus"):
         assert flag in r.stdout
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with the agreed keys."""
+    import json
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-envs-per-core", "1", "--cpu-steps", "20"], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "env-substeps/s" and line["unit"] == "env-substeps/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "env-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
