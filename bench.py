@@ -144,7 +144,19 @@ def b200_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the first communicator comes up; stdout must carry exactly
+        # one JSON line, so fd 1 points at stderr until the communicator exists.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     rb._lib.load()
     tdtype = torch.float64 if args.dtype == "fp64" else torch.float32
     esize = 8 if args.dtype == "fp64" else 4

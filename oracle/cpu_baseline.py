@@ -68,7 +68,7 @@ def python_port_sphere_incline(sample, cores=None, envs_per_core=16, steps=400):
         res = pool.map(_worker, jobs, chunksize=1)
         wall = time.perf_counter() - t0
     env_steps = sum(r[0] for r in res)
-    return {"value": env_steps / wall, "unit": "env-steps/s", "cores": cores, "kind": "port",
+    return {"value": env_steps / wall, "unit": "env-substeps/s", "cores": cores, "kind": "port",
             "sample": f"{n} envs x {steps} steps of the sphere-on-incline workload, Python/NumPy port of the reference step "
                       f"under the fake MuJoCo, {cores} processes, wall {wall:.2f} s",
             "per_core": env_steps / wall / cores, "wall_s": wall}
@@ -89,5 +89,5 @@ def c_port_sphere_incline(sample, steps=200, threads=None):
     t0 = time.perf_counter()
     co.step_body_plane(qp, qv, steps, **kw)
     wall = time.perf_counter() - t0
-    return {"value": E * steps / wall, "unit": "env-steps/s", "cores": threads, "kind": "port-native",
+    return {"value": E * steps / wall, "unit": "env-substeps/s", "cores": threads, "kind": "port-native",
             "sample": f"{E} envs x {steps} steps, C restatement (gcc -O2 -ffp-contract=off, OpenMP {threads} threads), wall {wall:.2f} s"}
