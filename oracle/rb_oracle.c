@@ -4,6 +4,11 @@
  * double (_f64, the reference's precision) and float (_f32, checker for the fp32 GPU mode).
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off [-fopenmp] -shared -fPIC).
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load the result.
+ *
+ * Pinning: the reference ships no tests of its own (tests/test_simulation.py is 0 bytes), so this restatement is
+ * pinned against outputs of the UNMODIFIED reference run in the build container under the fake MuJoCo backend
+ * (oracle/make_golden.py -> tests/golden/*.json; checked by tests/test_oracle_golden.py), which in turn reproduce
+ * the two published plots that match the shipped code.  Parity against the real MuJoCo C library is unverified.
  */
 #include <math.h>
 #include <stdlib.h>

@@ -302,17 +302,27 @@ int workspace(size_t bytes, void **out) {
 constexpr int kMaxChunks = 8;
 struct Pipe {
     bool ready = false;
+    int device = -1;
     int sm_count = 148;
     cudaStream_t in = nullptr, out = nullptr, compute[2] = {nullptr, nullptr};
     cudaEvent_t start = nullptr, finished = nullptr, arrived[kMaxChunks] = {}, stepped[kMaxChunks] = {};
 } g_pipe;
 
+// One process drives one GPU: the driver's streams and workspace live on the device that was
+// current at the first host-buffer call, and a call made with another device current is refused.
 int pipe_init() {
-    if (g_pipe.ready) return RBS_OK;
-    cudaError_t err = cudaSuccess;
     int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(RBS_ECUDA, "no CUDA device");
+    }
+    if (g_pipe.ready) {
+        if (dev != g_pipe.device)
+            return fail(RBS_EINVAL, "host-buffer driver is bound to device %d of this process, current device is %d", g_pipe.device, dev);
+        return RBS_OK;
+    }
+    cudaError_t err = cudaSuccess;
     auto ok = [&](cudaError_t e) { if (err == cudaSuccess) err = e; };
-    ok(cudaGetDevice(&dev));
     ok(cudaDeviceGetAttribute(&g_pipe.sm_count, cudaDevAttrMultiProcessorCount, dev));
     ok(cudaStreamCreateWithFlags(&g_pipe.in, cudaStreamNonBlocking));
     ok(cudaStreamCreateWithFlags(&g_pipe.out, cudaStreamNonBlocking));
@@ -325,6 +335,7 @@ int pipe_init() {
         ok(cudaEventCreateWithFlags(&g_pipe.stepped[i], cudaEventDisableTiming));
     }
     if (err != cudaSuccess) return fail(RBS_ECUDA, "pipeline resources: %s", cudaGetErrorString(err));
+    g_pipe.device = dev;
     g_pipe.ready = true;
     return RBS_OK;
 }
@@ -343,6 +354,8 @@ int run_host(const Args *a, int n_body, int body_fastest, void *qpos_host, void 
     if (a->n_env == 0) return RBS_OK;
     if (!qpos_host || !qvel_host) return fail(RBS_EINVAL, "null host buffer");
     std::lock_guard<std::mutex> lock(g_ws_mutex);
+    int rc0 = pipe_init();
+    if (rc0) return rc0;
     const size_t es = elem_size(a->dtype);
     const size_t nb = (size_t)a->n_env * n_body;
     const size_t qpos_bytes = nb * 7 * es, qvel_bytes = nb * 6 * es, state_bytes = nb * 13 * es;
@@ -561,12 +574,12 @@ int rbs_run_body_plane_host(const rbs_body_plane_args *a, void *qpos_host, void 
     std::lock_guard<std::mutex> lock(g_ws_mutex);
     const size_t es = elem_size(a->dtype);
     const long E = a->n_env;
+    rc = pipe_init();
+    if (rc) return rc;
     void *base = nullptr;
     rc = workspace((size_t)E * 26 * es, &base);
     if (rc) return rc;
     char *qpos_d = static_cast<char *>(base), *qvel_d = qpos_d + (size_t)E * 7 * es, *state_d = qvel_d + (size_t)E * 6 * es;
-    rc = pipe_init();
-    if (rc) return rc;
     // chunk = a whole number of full waves of CTAs, so that no chunk ends in a ragged partial wave
     long chunk = (E + kMaxChunks - 1) / kMaxChunks;
     const long quantum = (long)g_pipe.sm_count * 4 * rbs::kBlock;

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import (RBS_F32, RBS_F64, RBS_GEOM_BOX, RBS_GEOM_SPHERE, RBS_INERTIA_GENERAL, RBS_INERTIA_ISOTROPIC,
-                   RBS_SCHEME_A, RBS_SCHEME_GENERAL, BodyPlaneArgs, MultiSphereArgs, TwoBallArgs)
+                   RBS_SCHEME_A, BodyPlaneArgs, MultiSphereArgs, TwoBallArgs)
 
 
 def rbs_dtype(dtype):

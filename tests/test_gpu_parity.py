@@ -644,3 +644,22 @@ def test_padded_stride_and_applied_wrench_per_env(rb):
     got = big[:, :E].cpu().numpy()
     assert np.isnan(big[:, E:].cpu().numpy()).all()                       # the padding is never touched
     assert comp_rel_err(got[:7].T, qp, 1e-3) <= 1e-11 and comp_rel_err(got[7:].T, qv, 1e-3) <= 1e-11
+
+
+def test_headless_loop_batched_logger_and_cli(rb, capsys):
+    """start_main_loop's contract with a batch: the device-side TrajectoryLog of env 0 equals the one-env run, and
+    the headless CLI reports the same final state as the scenario module."""
+    import json
+    from rigidbody_simulation_b200.src import simulate
+    from rigidbody_simulation_b200.src.simulation import single_sphere_bounce
+    _, d1, log1 = single_sphere_bounce.run_headless(steps=150, nenv=1)
+    _, d8, log8 = single_sphere_bounce.run_headless(steps=150, nenv=8)
+    assert log8.buf.shape == (150, 4, 3)
+    assert np.array_equal(np.array(log1.z_positions), np.array(log8.z_positions))
+    assert np.array_equal(np.asarray(d1.qpos), d8.qpos.torch().cpu().numpy()[5])
+    out = simulate.run_simulation("single_sphere", steps=150, envs=3)
+    assert out["qpos_env0"] == np.asarray(d1.qpos).tolist()
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["sim"] == "single_sphere" and line["envs"] == 3
+    with pytest.raises(SystemExit):
+        simulate.run_simulation("compare_builtin")
