@@ -313,13 +313,13 @@ def b200_arm(args):
                          "impulses_per_env_substep": i_per, "launch_ms": launch_ms, "substeps_per_launch": F,
                          "hbm_GBps_of_same_launch": fused_gbs,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture
-                         # summarised in profiles/r1_summary.md (valid for the default 1,048,576-env fp64 shape only)
-                         "traffic": 176.1e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
+                         # in profiles/r1_ncu_full_fast_kernel.csv (valid for the default 1,048,576-env fp64 shape only)
+                         "traffic": 194.2e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
             "roofline_k1": {"bound": "hbm", "kernel": "same kernel, 1 substep per launch (the reference's per-frame call)",
                             "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
                             "peak_source": hbm_src, "bytes_per_env": (26 + 2) * esize, "launch_ms": k1_launch_ms,
                             "env_steps_per_s": world * E / (k1_launch_ms * 1e-3),
-                            "traffic": 177.6e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
+                            "traffic": 185.9e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
         }
         line["end_of_run_stats"] = stats
         line["other_policies"] = {
