@@ -1,12 +1,8 @@
 #!/bin/bash
-# Scratch tuning sweep (kept for the record): arithmetic policy x occupancy x fuse factor of the headline kernel.
-for arith in fast strict; do
-for minb in 4 6 8; do
-  for fuse in 64 256; do
-    RBS_MINB=$minb python bench.py --no-cpu-baseline --steps 3 --warmup 2 --fuse $fuse --arith $arith 2>/dev/null | python -c "
+# Scratch tuning sweep (kept for the record): occupancy variants of the fast headline kernel.
+for minb in 4 5 6 8; do
+    RBS_MINB=$minb python bench.py --no-cpu-baseline --steps 4 --warmup 3 --arith fast 2>/dev/null | python -c "
 import sys, json
 d = json.loads(sys.stdin.read())
-print('arith=$arith minb=$minb fuse=$fuse value=%.3e ms=%.2f frac=%.3f k1_GBps=%.0f k1_us=%.1f e2e=%.3e' % (d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline_k1']['achieved'], d['roofline_k1']['launch_ms']*1e3, d['e2e']['value']))"
-  done
-done
+print('fast minb=$minb value=%.4e ms=%.3f frac=%.3f k1_GBps=%.0f e2e=%.3e' % (d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline_k1']['achieved'], d['e2e']['value']))"
 done

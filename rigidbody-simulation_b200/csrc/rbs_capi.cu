@@ -83,12 +83,12 @@ template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_a
 
 // Resident CTAs per SM the headline kernels are compiled for (register cap 65536 / (128 * MINB)).
 // Measured on B200, 1M envs fp64 (profiles/r1_summary.md): strict policy -- fused launches fastest at 6 (80 regs),
-// the one-substep streaming launch at 8 (64 regs, more loads in flight); fast policy -- fused at 4, streaming at 6.
+// the one-substep streaming launch at 8 (64 regs, more loads in flight); fast policy -- 6 (79 regs, no spills) for both.
 // RBS_MINB overrides for experiments.
 int tuning_minb(int substeps, int arith) {
     static int forced = [] { const char *e = getenv("RBS_MINB"); return e ? atoi(e) : 0; }();
     if (forced) return forced;
-    if (arith == RBS_ARITH_FAST) return substeps <= 2 ? 6 : 4;
+    if (arith == RBS_ARITH_FAST) return 6;
     return substeps <= 2 ? 8 : 6;
 }
 
@@ -120,6 +120,7 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
     }
     switch (tuning_minb(a->substeps, RBS_ARITH_FAST)) {
         case 4: rbs::step_sphere_plane_fast_kernel<T, 4, false><<<grid, rbs::kBlock, 0, st>>>(p); break;
+        case 5: rbs::step_sphere_plane_fast_kernel<T, 5, false><<<grid, rbs::kBlock, 0, st>>>(p); break;
         case 6: rbs::step_sphere_plane_fast_kernel<T, 6, false><<<grid, rbs::kBlock, 0, st>>>(p); break;
         default: rbs::step_sphere_plane_fast_kernel<T, 8, false><<<grid, rbs::kBlock, 0, st>>>(p); break;
     }
