@@ -134,6 +134,8 @@ RBS_API int rbs_step_body_plane(const rbs_body_plane_args *a);
 typedef struct rbs_two_ball_args {
     int dtype;
     int substeps;
+    int arith;                 /* RBS_ARITH_STRICT | RBS_ARITH_FAST */
+    int reserved;
     long n_env;
     long stride;
     void *state;               /* [13][2][stride], env-major */

@@ -66,9 +66,10 @@ for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
     s = synth.two_ball(E)
     model, data = ball_collision.build(E, device=dev, dtype=dtype)
     data.set_state(s["qpos"], s["qvel"])
-    for K in (1, 64):
-        f = lambda: stepper.step_two_ball(model, data, 0.01, 1.0, 0.3, radius=0.1, substeps=K, count=False)
-        report(f"cfg3 two_ball {tag} strict", E, 2, K, timed(f))
+    for arith in ("strict", "fast"):
+        for K in (1, 64):
+            f = lambda: stepper.step_two_ball(model, data, 0.01, 1.0, 0.3, radius=0.1, substeps=K, count=False, arith=arith)
+            report(f"cfg3 two_ball {tag} {arith}", E, 2, K, timed(f))
     # config 5 multi sphere (8192 envs = the per-GPU shard of 65536 over 8 GPUs; and the whole 65536) ------------
     for E5 in ((8192, 65536) if not quick else (1024,)):
         s = synth.multi_sphere(E5, n_body=64, friction=0.0)

@@ -44,7 +44,8 @@ class BodyPlaneArgs(Structure):
 class TwoBallArgs(Structure):
     """struct rbs_two_ball_args"""
     _fields_ = [
-        ("dtype", c_int), ("substeps", c_int), ("n_env", c_long), ("stride", c_long),
+        ("dtype", c_int), ("substeps", c_int), ("arith", c_int), ("reserved", c_int),
+        ("n_env", c_long), ("stride", c_long),
         ("state", c_void_p),
         ("mass", c_void_p), ("mass_u", D2),
         ("radius", c_void_p), ("radius_u", c_double),

@@ -196,6 +196,7 @@ int validate_two_ball(const rbs_two_ball_args *a, bool need_state) {
     if (bad_dtype(a->dtype)) return fail(RBS_EINVAL, "rbs_step_two_ball: dtype %d is not RBS_F32/RBS_F64", a->dtype);
     if (a->n_env < 0) return fail(RBS_EINVAL, "rbs_step_two_ball: n_env %ld < 0", a->n_env);
     if (a->substeps < 1) return fail(RBS_EINVAL, "rbs_step_two_ball: substeps %d < 1", a->substeps);
+    if (a->arith != RBS_ARITH_STRICT && a->arith != RBS_ARITH_FAST) return fail(RBS_EINVAL, "rbs_step_two_ball: bad arith %d", a->arith);
     if (need_state) {
         if (a->n_env > 0 && !a->state) return fail(RBS_EINVAL, "rbs_step_two_ball: null state");
         if (a->stride < a->n_env) return fail(RBS_EINVAL, "rbs_step_two_ball: stride %ld < n_env %ld", a->stride, a->n_env);
@@ -518,10 +519,15 @@ int rbs_step_two_ball(const rbs_two_ball_args *a) {
     if (rc) return rc;
     if (a->n_env == 0) return RBS_OK;
     const unsigned grid = blocks_for(a->n_env, rbs::kBlock);
-    if (a->dtype == RBS_F64)
-        rbs::step_two_ball_kernel<double><<<grid, rbs::kBlock, 0, as_stream(a->stream)>>>(make_params<double>(a));
-    else
-        rbs::step_two_ball_kernel<float><<<grid, rbs::kBlock, 0, as_stream(a->stream)>>>(make_params<float>(a));
+    cudaStream_t st = as_stream(a->stream);
+    if (a->arith == RBS_ARITH_FAST) {
+        if (a->dtype == RBS_F64) rbs::step_two_ball_fast_kernel<double><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a));
+        else rbs::step_two_ball_fast_kernel<float><<<grid, rbs::kBlock, 0, st>>>(make_params<float>(a));
+    } else if (a->dtype == RBS_F64) {
+        rbs::step_two_ball_kernel<double><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a));
+    } else {
+        rbs::step_two_ball_kernel<float><<<grid, rbs::kBlock, 0, st>>>(make_params<float>(a));
+    }
     return check_launch("rbs_step_two_ball");
 }
 

@@ -31,12 +31,13 @@ def build(nenv=1, device=None, dtype=torch.float64):
 
 
 def step_with_custom_collisions(model, data, dt=0.01, substeps=1, restitution=restitution,
-                                friction_coefficient=friction_coefficient, ball_radius=ball_radius):
+                                friction_coefficient=friction_coefficient, ball_radius=ball_radius, arith="strict"):
     """Gravity on both balls, ball-ground impulses with the z clamp, the one-sided ball-ball impulse with the
     symmetric positional correction, explicit position integration; quaternions untouched (:73-125).
     Returns both ball positions like the reference (:125)."""
     mj.mj_forward(model, data)                               # :74 (no effect on the results there either)
-    stepper.step_two_ball(model, data, dt, restitution, friction_coefficient, radius=ball_radius, substeps=substeps)
+    stepper.step_two_ball(model, data, dt, restitution, friction_coefficient, radius=ball_radius, substeps=substeps,
+                          arith=arith)
     rows = data.rows(0, 3)                                   # [3, 2, E]
     if data.squeeze:
         host = rows[:, :, 0].cpu().numpy()

@@ -117,12 +117,12 @@ def step_body_plane(model, data, body_id, dt, restitution, friction_coeff, conta
     _lib.check(_lib.load().rbs_step_body_plane(ctypes.byref(a)))
 
 
-def two_ball_args(model, data, dt, restitution, friction, radius, substeps, count=True):
+def two_ball_args(model, data, dt, restitution, friction, radius, substeps, count=True, arith="strict"):
     _require_cuda(model)
     if model.nfree != 2 or data.layout != "env":
         raise ValueError("the two-ball step needs a scene with exactly two free bodies (ball_collision.xml shape)")
     a = TwoBallArgs()
-    a.dtype, a.substeps = rbs_dtype(model.dtype), int(substeps)
+    a.dtype, a.substeps, a.arith = rbs_dtype(model.dtype), int(substeps), ARITH[arith]
     a.n_env, a.stride = data.nenv, data.stride
     a.state = _ptr(data.state)
     pe = model.per_env
@@ -136,8 +136,8 @@ def two_ball_args(model, data, dt, restitution, friction, radius, substeps, coun
     return a
 
 
-def step_two_ball(model, data, dt, restitution, friction, radius=0.1, substeps=1, count=True):
-    a = two_ball_args(model, data, dt, restitution, friction, radius, substeps, count)
+def step_two_ball(model, data, dt, restitution, friction, radius=0.1, substeps=1, count=True, arith="strict"):
+    a = two_ball_args(model, data, dt, restitution, friction, radius, substeps, count, arith)
     a.stream = current_stream(model.device)
     _lib.check(_lib.load().rbs_step_two_ball(ctypes.byref(a)))
 

@@ -380,6 +380,41 @@ def test_two_ball_100k_vs_oracle(rb, dtype, tol):
     assert hits[1].sum() > E // 2        # most envs did collide
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float64, F64_STEP), (np.float32, F32_STEP)])
+def test_two_ball_fast_policy_vs_oracle(rb, dtype, tol, golden):
+    from rigidbody_simulation_b200 import stepper, synth
+    from rigidbody_simulation_b200.src.simulation import ball_collision
+    E = 100_000
+    s = synth.two_ball(E)
+    model, data = ball_collision.build(E, dtype=tdt(dtype))
+    data.set_state(s["qpos"], s["qvel"])
+    qp, qv = s["qpos"].astype(dtype), s["qvel"].astype(dtype)
+    hits = (np.zeros(E, np.uint32), np.zeros(E, np.uint32))
+    m = float(model.body_mass[1])
+    done = 0
+    floor = 1e-3 if dtype == np.float64 else 1e-2
+    for upto in (1, 150):
+        co.step_two_ball(qp, qv, upto - done, mass=[m, m], radius=0.1, gravity=G, dt=0.01, restitution=1.0, friction=0.3, counters=hits)
+        stepper.step_two_ball(model, data, 0.01, 1.0, 0.3, radius=0.1, substeps=upto - done, arith="fast")
+        done = upto
+        gq, gv = state_of(data)
+        err = max(comp_rel_err(gq, qp, floor), comp_rel_err(gv, qv, floor))
+        if upto == 1:
+            assert err <= tol, (upto, err)
+        elif dtype == np.float64:          # fp32 trajectories part ways at the ball-ball impact (7 significant digits)
+            assert err <= 1e-7, (upto, err)
+        else:
+            assert np.isfinite(gq).all() and np.isfinite(gv).all()
+    if dtype == np.float64:
+        same = (data.n_contacts[:E].cpu().numpy() == hits[0]) & (data.n_impulses[:E].cpu().numpy() == hits[1])
+        assert same.mean() >= 0.9999, same.mean()
+        # shipped script under the fast policy: same final state to 1e-9
+        g = golden("script_ball_collision_500")
+        model, data = ball_collision.build(1)
+        ball_collision.step_with_custom_collisions(model, data, 0.01, substeps=500, arith="fast")
+        assert np.max(np.abs(np.asarray(data.qpos) - g["qpos"])) < 1e-9
+
+
 # ------------------------------------------------------------------------------------ multi sphere
 def test_multi_sphere_golden(rb, golden):
     from rigidbody_simulation_b200.src.simulation import multi_sphere_bounce as ms
