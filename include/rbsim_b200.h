@@ -107,6 +107,9 @@ typedef struct rbs_body_plane_args {
     int inertia_mode;          /* RBS_INERTIA_ISOTROPIC is valid only when the three principal moments are equal */
     long n_env;
     long stride;               /* elements between state rows, >= n_env */
+    long param_stride;         /* row stride of the multi-row per-env arrays (inertia, size, xfrc); 0 = n_env.
+                                  Lets a call cover a window of a larger batch: offset every pointer by the
+                                  window start, pass the window length as n_env and the batch size here. */
     int substeps;              /* >= 1 */
     int arith;                 /* RBS_ARITH_STRICT: the reference's rounding sequence (bit-faithful);
                                   RBS_ARITH_FAST: FMA / reciprocal-multiply re-association, <= 1e-12 per step in

@@ -26,7 +26,7 @@ class BodyPlaneArgs(Structure):
     """struct rbs_body_plane_args"""
     _fields_ = [
         ("dtype", c_int), ("geom", c_int), ("scheme", c_int), ("inertia_mode", c_int),
-        ("n_env", c_long), ("stride", c_long), ("substeps", c_int), ("arith", c_int),
+        ("n_env", c_long), ("stride", c_long), ("param_stride", c_long), ("substeps", c_int), ("arith", c_int),
         ("state", c_void_p),
         ("mass", c_void_p), ("mass_u", c_double),
         ("inertia", c_void_p), ("inertia_u", D3),

@@ -55,7 +55,7 @@ template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_a
     auto at = [&](const void *base) { return base ? static_cast<const T *>(base) + w.off : nullptr; };
     p.n_env = w.cnt;
     p.stride = w.stride;
-    p.pstride = a->n_env;
+    p.pstride = a->param_stride > 0 ? a->param_stride : a->n_env;
     p.substeps = a->substeps;
     p.state = static_cast<T *>(w.state);
     p.mass = at(a->mass);
@@ -161,6 +161,8 @@ int validate_body_plane(const rbs_body_plane_args *a, bool need_state) {
         return fail(RBS_EINVAL, "rbs_step_body_plane: RBS_ARITH_FAST is implemented for scheme A + isotropic inertia only");
     if (a->n_env < 0) return fail(RBS_EINVAL, "rbs_step_body_plane: n_env %ld < 0", a->n_env);
     if (a->substeps < 1) return fail(RBS_EINVAL, "rbs_step_body_plane: substeps %d < 1", a->substeps);
+    if (a->param_stride != 0 && a->param_stride < a->n_env)
+        return fail(RBS_EINVAL, "rbs_step_body_plane: param_stride %ld < n_env %ld", a->param_stride, a->n_env);
     if (need_state) {
         if (a->n_env > 0 && !a->state) return fail(RBS_EINVAL, "rbs_step_body_plane: null state");
         if (a->stride < a->n_env) return fail(RBS_EINVAL, "rbs_step_body_plane: stride %ld < n_env %ld", a->stride, a->n_env);

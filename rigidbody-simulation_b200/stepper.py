@@ -50,9 +50,14 @@ def _require_cuda(model):
 ARITH = {"strict": _lib.RBS_ARITH_STRICT, "fast": _lib.RBS_ARITH_FAST}
 
 
+def _shift(ptr, elements, itemsize):
+    return None if ptr is None or ptr.value is None else ctypes.c_void_p(ptr.value + elements * itemsize)
+
+
 def body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold, scheme, substeps,
-                    count=True, strict_inertia=None, arith="strict"):
-    """rbs_body_plane_args for the single free body ``body_id`` of ``model`` resting on its plane."""
+                    count=True, strict_inertia=None, arith="strict", env_range=None):
+    """rbs_body_plane_args for the single free body ``body_id`` of ``model`` resting on its plane.
+    ``env_range=(start, count)`` restricts the call to a window of the environments."""
     _require_cuda(model)
     if model.nfree != 1 or data.layout != "env":
         raise ValueError("this step function handles scenes with exactly one free body (sphere.xml / cube.xml shape)")
@@ -103,18 +108,61 @@ def body_plane_args(model, data, body_id, dt, restitution, friction_coeff, conta
     a.contact_threshold = float(contact_threshold)
     a.n_contacts = _ptr(data.n_contacts) if count else None
     a.n_impulses = _ptr(data.n_impulses) if count else None
+    if env_range is not None:
+        off, cnt = int(env_range[0]), int(env_range[1])
+        if off < 0 or cnt < 0 or off + cnt > data.nenv:
+            raise ValueError(f"env_range {env_range} outside 0..{data.nenv}")
+        es = 8 if model.dtype == torch.float64 else 4
+        a.n_env, a.param_stride = cnt, data.nenv
+        for name in ("state", "mass", "inertia", "size", "restitution", "friction", "xfrc"):
+            setattr(a, name, _shift(ctypes.c_void_p(getattr(a, name)), off, es))
+        for name in ("n_contacts", "n_impulses"):
+            setattr(a, name, _shift(ctypes.c_void_p(getattr(a, name)), off, 4))
     a._keep = keep
     return a
 
 
 def step_body_plane(model, data, body_id, dt, restitution, friction_coeff, contact_threshold,
-                    scheme=RBS_SCHEME_A, substeps=1, count=True, strict_inertia=None, arith="strict"):
+                    scheme=RBS_SCHEME_A, substeps=1, count=True, strict_inertia=None, arith="strict", env_range=None):
     """arith: "strict" reproduces the reference's rounding sequence; "fast" re-associates for the FP pipe
-    (sphere + scheme A + isotropic inertia only; <= 1e-12 relative per step in fp64)."""
+    (scheme A + isotropic inertia only; <= 1e-12 relative per step in fp64)."""
     a = body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold, scheme, substeps,
-                        count, strict_inertia, arith)
+                        count, strict_inertia, arith, env_range)
     a.stream = current_stream(model.device)
     _lib.check(_lib.load().rbs_step_body_plane(ctypes.byref(a)))
+
+
+class SplitChains:
+    """Run the fused launches of a long horizon as ``parts`` independent chains of environment windows, each on its
+    own stream.  Environments never interact, so the chains need no ordering between them; their launches interleave
+    on the device and the ragged last wave of CTAs of one chain's launch is filled by the other chain's work.
+
+        chains = SplitChains(model, data); chains.fork()
+        for _ in range(n): chains.step(dt=..., substeps=128, ...)      # same keywords as step_body_plane
+        chains.join()
+    """
+
+    def __init__(self, model, data, parts=2, align=128):
+        self.model, self.data = model, data
+        per = -(-data.nenv // parts)
+        per = -(-per // align) * align
+        self.ranges = [(o, min(per, data.nenv - o)) for o in range(0, data.nenv, per)]
+        self.streams = [torch.cuda.Stream(device=model.device) for _ in self.ranges]
+
+    def fork(self):
+        cur = torch.cuda.current_stream(self.model.device)
+        for st in self.streams:
+            st.wait_stream(cur)
+
+    def step(self, body_id=-1, **kw):
+        for rng, st in zip(self.ranges, self.streams):
+            with torch.cuda.stream(st):
+                step_body_plane(self.model, self.data, body_id, env_range=rng, **kw)
+
+    def join(self):
+        cur = torch.cuda.current_stream(self.model.device)
+        for st in self.streams:
+            cur.wait_stream(st)
 
 
 def two_ball_args(model, data, dt, restitution, friction, radius, substeps, count=True, arith="strict"):

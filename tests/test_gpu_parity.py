@@ -698,3 +698,40 @@ def test_headless_loop_batched_logger_and_cli(rb, capsys):
     assert line["sim"] == "single_sphere" and line["envs"] == 3
     with pytest.raises(SystemExit):
         simulate.run_simulation("compare_builtin")
+
+
+def test_env_windows_and_split_chains(rb):
+    """A call restricted to a window of the batch (env_range) touches only that window and computes what the whole-batch
+    call computes there, including per-env parameter rows ([3][E] sizes) and counters; SplitChains == one chain."""
+    from rigidbody_simulation_b200 import stepper, synth
+    E = 70_001
+    s = synth.cube(E, kind="bounce")
+    rng = np.random.default_rng(11)
+    size = (0.4 + rng.uniform(-0.05, 0.05, (1, E))).repeat(3, axis=0)         # per-env cube half sizes, [3, E]
+
+    def fresh():
+        model, data = make_single(rb, "box", s["half"], 0.0, s["qpos"], s["qvel"])
+        model.set_per_env(size=size)
+        return model, data
+
+    kw = dict(dt=0.009, restitution=0.2, friction_coeff=0.6, contact_threshold=1e-4, strict_inertia=False)
+    model, whole = fresh()
+    for _ in range(3):
+        stepper.step_body_plane(model, whole, -1, substeps=40, **kw)
+    model, data = fresh()
+    before = data.state.clone()
+    stepper.step_body_plane(model, data, -1, substeps=40, env_range=(1000, 5000), **kw)
+    assert torch.equal(data.state[:, :, :1000], before[:, :, :1000]) and torch.equal(data.state[:, :, 6000:], before[:, :, 6000:])
+    assert not torch.equal(data.state[:, :, 1000:6000], before[:, :, 1000:6000])
+    model, data = fresh()
+    chains = stepper.SplitChains(model, data, parts=3)
+    assert sum(c for _, c in chains.ranges) == E
+    chains.fork()
+    for _ in range(3):
+        chains.step(substeps=40, **kw)
+    chains.join()
+    torch.cuda.synchronize()
+    assert torch.equal(data.state, whole.state)
+    assert torch.equal(data.n_contacts, whole.n_contacts) and int(whole.n_contacts.sum()) > 0
+    with pytest.raises(ValueError):
+        stepper.step_body_plane(model, data, -1, substeps=1, env_range=(E - 10, 20), **kw)
