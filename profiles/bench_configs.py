@@ -33,9 +33,29 @@ def timed(fn, reps=5, warm=2):
     return float(np.median(ms))
 
 
-def report(name, E, B, K, ms, extra=""):
-    print(json.dumps({"config": name, "envs": E, "bodies_per_env": B, "substeps_per_launch": K, "launch_ms": round(ms, 4),
-                      "env_substeps_per_s": E * K / (ms * 1e-3), "body_substeps_per_s": E * B * K / (ms * 1e-3), "note": extra}), flush=True)
+PEAK = {}
+
+
+def report(name, E, B, K, ms, extra="", flops=None):
+    """flops = approximate algorithmic flops per body-substep (mul/add/div/sqrt = 1 each) from the measured contact
+    rates; the fraction is against the FMA-probe peak measured in this process."""
+    out = {"config": name, "envs": E, "bodies_per_env": B, "substeps_per_launch": K, "launch_ms": round(ms, 4),
+           "env_substeps_per_s": E * K / (ms * 1e-3), "body_substeps_per_s": E * B * K / (ms * 1e-3), "note": extra}
+    if flops is not None:
+        tf = out["body_substeps_per_s"] * flops / 1e12
+        dt = torch.float32 if "fp32" in name else torch.float64
+        if dt not in PEAK:
+            PEAK[dt] = stepper.fma_peak(dev, dt) / 1e12
+        out.update(flops_per_body_substep=round(flops, 1), tflops=round(tf, 2), fp_roofline_frac=round(tf / PEAK[dt], 3))
+    print(json.dumps(out), flush=True)
+
+
+def rates(data, n_units, K, fn):
+    """contacts / impulses per unit-substep over one counted launch of K substeps"""
+    data.n_contacts.zero_(); data.n_impulses.zero_()
+    fn()
+    torch.cuda.synchronize()
+    return float(data.n_contacts.sum()) / (n_units * K), float(data.n_impulses.sum()) / (n_units * K)
 
 
 for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
@@ -51,7 +71,8 @@ for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
             f = lambda: stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=K, count=False, arith=arith)
             for _ in range(8):
                 stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=128, count=False, arith=arith)
-            report(f"cfg2 sphere_incline {tag} {arith}", E, 1, K, timed(f))
+            c, i = rates(data, E, K, lambda: stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=K, count=True, arith=arith))
+            report(f"cfg2 sphere_incline {tag} {arith}", E, 1, K, timed(f), flops=60 + 72 * i + 22 * (c - i))
     # config 4 cube ------------------------------------------------------------------------------------------
     for kind in ("bounce", "incline"):
         s = synth.cube(E, kind=kind)
@@ -61,7 +82,9 @@ for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
         for arith in ("strict", "fast"):
             for K in (1, 64):
                 f = lambda: stepper.step_body_plane(model, data, -1, s["dt"], 0.2, 0.6, 1e-4, substeps=K, count=False, arith=arith)
-                report(f"cfg4 cube_{kind} {tag} {arith}", E, 1, K, timed(f))
+                c, i = rates(data, E, K, lambda: stepper.step_body_plane(model, data, -1, s["dt"], 0.2, 0.6, 1e-4, substeps=K, count=True, arith=arith))
+                # free flight 60 + vertex scan (rotation 42 + 8 x 23) + per contact: arm 9 + impulse 72 / separating 22
+                report(f"cfg4 cube_{kind} {tag} {arith}", E, 1, K, timed(f), flops=60 + 226 + 81 * i + 31 * (c - i))
     # config 3 two balls ---------------------------------------------------------------------------------------
     s = synth.two_ball(E)
     model, data = ball_collision.build(E, device=dev, dtype=dtype)
@@ -69,7 +92,9 @@ for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
     for arith in ("strict", "fast"):
         for K in (1, 64):
             f = lambda: stepper.step_two_ball(model, data, 0.01, 1.0, 0.3, radius=0.1, substeps=K, count=False, arith=arith)
-            report(f"cfg3 two_ball {tag} {arith}", E, 2, K, timed(f))
+            c, i = rates(data, E, K, lambda: stepper.step_two_ball(model, data, 0.01, 1.0, 0.3, radius=0.1, substeps=K, count=True, arith=arith))
+            # per env: gravity 6 + ground tests 2 + pair test 12 + integrate 12; ~120 per ground impulse, ~190 per pair hit
+            report(f"cfg3 two_ball {tag} {arith}", E, 2, K, timed(f), flops=(32 + 120 * c + 190 * i) / 2)
     # config 5 multi sphere (8192 envs = the per-GPU shard of 65536 over 8 GPUs; and the whole 65536) ------------
     for E5 in ((8192, 65536) if not quick else (1024,)):
         s = synth.multi_sphere(E5, n_body=64, friction=0.0)
@@ -78,4 +103,6 @@ for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
         for arith in ("strict", "fast"):
             for K in (1, 16):
                 f = lambda: stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.0, substeps=K, count=False, arith=arith)
-                report(f"cfg5 multi_sphere64 {tag} {arith}", E5, 64, K, timed(f, reps=3, warm=1))
+                c, i = rates(data, E5 * 64, K, lambda: stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.0, substeps=K, count=True, arith=arith))
+                # per body: free flight 53 + ground test 7 + 63 pair rejects x 9 + per contact: exact narrow phase 25 + impulse 72 / 22
+                report(f"cfg5 multi_sphere64 {tag} {arith}", E5, 64, K, timed(f, reps=3, warm=1), flops=60 + 567 + 97 * i + 47 * (c - i))
