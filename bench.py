@@ -299,8 +299,7 @@ def b200_arm(args):
     k1_gbs = bytes_per_launch / (k1_launch_ms * 1e-3) / 1e9
 
     # --- optional end-of-run gather of logged statistics: the only collective in the whole job -------------------
-    stats = shard.gather_stats(shard.local_stats(data, float(model.body_mass[-1]), float(model.opt.gravity[2])),
-                               env_substeps=E * S * args.steps)
+    stats = shard.gather_stats(shard.local_stats(model, data), env_substeps=E * S * args.steps)
 
     if rank == 0:
         line = {

@@ -206,6 +206,19 @@ RBS_API int rbs_run_multi_sphere_host(const rbs_multi_sphere_args *a, void *qpos
 RBS_API int rbs_release_workspace(void);
 
 /* ---------------------------------------------------------------------------------------------
+ * Run statistics in one pass (new behaviour; the reference only appends positions to Python lists,
+ * src/visualization/logger_base.py:22-32).  `state` holds n_bodies columns with row stride `stride` (either
+ * layout flattened: n_bodies = n_env * n_body).  out[5] (device, double) must be initialised by the caller with
+ * {0, 0, -1e300, 0, 0}; the call accumulates
+ *   out[0] += kinetic energy (linear + rotational), out[1] += potential energy -m g.p,
+ *   out[2]  = max height along -g (or +z when g = 0), out[3] += n_contacts, out[4] += n_impulses.
+ * mass [n_bodies] / inertia [3][inertia_stride] may be NULL (uniform values are used).
+ * --------------------------------------------------------------------------------------------- */
+RBS_API int rbs_stats(int dtype, long n_bodies, const void *state, long stride, const void *mass, double mass_u,
+                      const void *inertia, long inertia_stride, const double inertia_u[3], const double gravity[3],
+                      const unsigned *n_contacts, const unsigned *n_impulses, double *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement helper (not part of the reference's surface): a dependent-chain-free FMA loop used by
  * bench.py to measure the FP32 / FP64 CUDA-core peak of the device it runs on.
  * Writes nothing useful to `sink` (n_threads elements) but keeps the compiler honest.

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <mutex>
 
 #include "../../include/rbsim_b200.h"
@@ -650,6 +651,29 @@ int rbs_release_workspace(void) {
     g_ws = nullptr;
     g_ws_bytes = 0;
     return RBS_OK;
+}
+
+int rbs_stats(int dtype, long n_bodies, const void *state, long stride, const void *mass, double mass_u,
+              const void *inertia, long inertia_stride, const double inertia_u[3], const double gravity[3],
+              const unsigned *n_contacts, const unsigned *n_impulses, double *out, void *stream) {
+    if (bad_dtype(dtype)) return fail(RBS_EINVAL, "rbs_stats: bad dtype %d", dtype);
+    if (n_bodies < 0) return fail(RBS_EINVAL, "rbs_stats: n_bodies %ld < 0", n_bodies);
+    if (n_bodies == 0) return RBS_OK;
+    if (!state || !out || !inertia_u || !gravity) return fail(RBS_EINVAL, "rbs_stats: null argument");
+    if (stride < n_bodies) return fail(RBS_EINVAL, "rbs_stats: stride %ld < n_bodies %ld", stride, n_bodies);
+    const double gn = sqrt(gravity[0] * gravity[0] + gravity[1] * gravity[1] + gravity[2] * gravity[2]);
+    const double ux = gn > 0 ? -gravity[0] / gn : 0.0, uy = gn > 0 ? -gravity[1] / gn : 0.0, uz = gn > 0 ? -gravity[2] / gn : 1.0;
+    long blocks = (n_bodies + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (dtype == RBS_F64)
+        rbs::stats_kernel<double><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+            n_bodies, (const double *)state, stride, (const double *)mass, mass_u, (const double *)inertia, inertia_stride,
+            inertia_u[0], inertia_u[1], inertia_u[2], gravity[0], gravity[1], gravity[2], ux, uy, uz, n_contacts, n_impulses, out);
+    else
+        rbs::stats_kernel<float><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+            n_bodies, (const float *)state, stride, (const float *)mass, (float)mass_u, (const float *)inertia, inertia_stride,
+            inertia_u[0], inertia_u[1], inertia_u[2], gravity[0], gravity[1], gravity[2], ux, uy, uz, n_contacts, n_impulses, out);
+    return check_launch("rbs_stats");
 }
 
 int rbs_fma_probe(int dtype, long n_threads, int iters, void *sink, void *stream) {

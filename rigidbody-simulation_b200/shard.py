@@ -20,16 +20,31 @@ def shard_range(n_total, rank, world_size):
     return start, count
 
 
-def local_stats(data, mass, gravity_z):
-    """[n_env_substeps_placeholder, contacts, impulses, kinetic+potential energy sum, max height] for one rank."""
-    rows = data.rows(0, 13)                                           # [13, nfree, E]
-    v2 = (rows[7:10] ** 2).sum(dim=0)
-    # rotational energy needs the inertia; spheres/cubes of the reference are isotropic: callers pass mass only
-    ke = 0.5 * mass * v2.sum()
-    pe = -mass * gravity_z * rows[2].sum()
-    return torch.stack([torch.zeros((), dtype=torch.float64, device=rows.device),
-                        data.n_contacts.sum().to(torch.float64), data.n_impulses.sum().to(torch.float64),
-                        (ke + pe).to(torch.float64), rows[2].max().to(torch.float64)])
+def local_stats(model, data):
+    """[env-substeps placeholder, contacts, impulses, kinetic + potential energy sum, max height] for this rank's
+    environments, computed by one pass of the CUDA statistics kernel (rbs_stats) over the SoA state."""
+    import ctypes
+
+    from . import _lib
+    from .stepper import current_stream, rbs_dtype
+    if data.device.type != "cuda":
+        raise _lib.RbsError("run statistics are computed on a CUDA device only (no CPU fallback)")
+    out = torch.tensor([0.0, 0.0, -1.0e300, 0.0, 0.0], dtype=torch.float64, device=data.device)
+    n = data.nenv * data.nfree
+    pe = model.per_env
+    first = model.free_ids[0]
+    per_body = data.layout == "body" or data.nfree == 1          # per-env arrays line up with the flattened columns
+    mass_t = pe.get("mass") if per_body else None
+    inertia_t = pe.get("inertia") if per_body else None
+    if data.layout == "env" and data.nfree > 1 and any(model.body_mass[i] != model.body_mass[first] for i in model.free_ids):
+        raise ValueError("statistics of env-layout scenes need identical bodies")
+    I3 = (ctypes.c_double * 3)(*[float(v) for v in model.body_inertia[first]])
+    G3 = (ctypes.c_double * 3)(*[float(v) for v in model.opt.gravity])
+    P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    _lib.check(_lib.load().rbs_stats(rbs_dtype(model.dtype), n, P(data.state), n if data.layout == "env" else data.stride,
+                                     P(mass_t), float(model.body_mass[first]), P(inertia_t), n, I3, G3,
+                                     P(data.n_contacts), P(data.n_impulses), P(out), current_stream(model.device)))
+    return torch.stack([torch.zeros((), dtype=torch.float64, device=data.device), out[3], out[4], out[0] + out[1], out[2]])
 
 
 def gather_stats(stats, env_substeps):

@@ -735,3 +735,37 @@ def test_env_windows_and_split_chains(rb):
     assert torch.equal(data.n_contacts, whole.n_contacts) and int(whole.n_contacts.sum()) > 0
     with pytest.raises(ValueError):
         stepper.step_body_plane(model, data, -1, substeps=1, env_range=(E - 10, 20), **kw)
+
+
+def test_run_statistics_kernel(rb):
+    """rbs_stats (energy / max height / event totals in one pass) against a NumPy evaluation of the same sums."""
+    from rigidbody_simulation_b200 import shard, stepper, synth
+    from rigidbody_simulation_b200.src.simulation import multi_sphere_bounce as ms
+    E = 30_011
+    s = synth.cube(E, kind="bounce")
+    model, data = make_single(rb, "box", [0.3, 0.2, 0.1], 0.0, s["qpos"], s["qvel"])     # anisotropic: exercises R^T w
+    stepper.step_body_plane(model, data, -1, 0.009, 0.2, 0.6, 1e-4, substeps=150)
+    got = shard.local_stats(model, data).cpu().numpy()
+    qp, qv = state_of(data)
+    m, I = model.body_mass[-1], model.body_inertia[-1]
+    from scipy.spatial.transform import Rotation
+    R = Rotation.from_quat(qp[:, [4, 5, 6, 3]]).as_matrix()
+    wb = np.einsum("eji,ej->ei", R, qv[:, 3:6])
+    ke = 0.5 * m * (qv[:, :3] ** 2).sum() + 0.5 * (wb ** 2 * I).sum()
+    pe = m * 9.8 * qp[:, 2].sum()
+    calls, imps = data.counters()
+    assert got[1] == calls.sum() and got[2] == imps.sum() and calls.sum() > 0
+    assert got[3] == pytest.approx(ke + pe, rel=1e-10)
+    assert got[4] == pytest.approx(qp[:, 2].max(), rel=1e-14)
+    # thread-per-body layout
+    s = synth.multi_sphere(500, n_body=27)
+    model, data = ms.build(500, n_body=27)
+    data.set_state(s["qpos"], s["qvel"])
+    stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.3, substeps=30)
+    got = shard.local_stats(model, data).cpu().numpy()
+    qp, qv = state_of(data)
+    qp, qv = qp.reshape(-1, 7), qv.reshape(-1, 6)
+    m, I = model.body_mass[1], model.body_inertia[1][0]
+    ref = 0.5 * m * (qv[:, :3] ** 2).sum() + 0.5 * I * (qv[:, 3:] ** 2).sum() + m * 9.8 * qp[:, 2].sum()
+    assert got[3] == pytest.approx(ref, rel=1e-10) and got[4] == pytest.approx(qp[:, 2].max(), rel=1e-14)
+    assert got[1] == data.counters()[0].sum()
