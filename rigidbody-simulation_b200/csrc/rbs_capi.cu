@@ -680,8 +680,17 @@ int rbs_fma_probe(int dtype, long n_threads, int iters, void *sink, void *stream
     if (bad_dtype(dtype)) return fail(RBS_EINVAL, "rbs_fma_probe: bad dtype %d", dtype);
     if (n_threads <= 0 || n_threads % 256 || iters < 1 || !sink) return fail(RBS_EINVAL, "rbs_fma_probe: n_threads must be a positive multiple of 256");
     const unsigned grid = (unsigned)(n_threads / 256);
-    if (dtype == RBS_F64) rbs::fma_probe_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(iters, (double *)sink);
-    else rbs::fma_probe_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(iters, (float *)sink);
+    static int mode = [] { const char *e = getenv("RBS_PROBE_MODE"); return e ? atoi(e) : 1; }();
+    cudaStream_t st = as_stream(stream);
+    if (dtype == RBS_F64) {
+        if (mode == 0) rbs::fma_probe_kernel<double, 0><<<grid, 256, 0, st>>>(iters, (double *)sink, 0.999999, 1e-7);
+        else if (mode == 2) rbs::fma_probe_kernel<double, 2><<<grid, 256, 0, st>>>(iters, (double *)sink, 0.999999, 1e-7);
+        else rbs::fma_probe_kernel<double, 1><<<grid, 256, 0, st>>>(iters, (double *)sink, 0.999999, 1e-7);
+    } else {
+        if (mode == 0) rbs::fma_probe_kernel<float, 0><<<grid, 256, 0, st>>>(iters, (float *)sink, 0.999999f, 1e-7f);
+        else if (mode == 2) rbs::fma_probe_kernel<float, 2><<<grid, 256, 0, st>>>(iters, (float *)sink, 0.999999f, 1e-7f);
+        else rbs::fma_probe_kernel<float, 1><<<grid, 256, 0, st>>>(iters, (float *)sink, 0.999999f, 1e-7f);
+    }
     return check_launch("rbs_fma_probe");
 }
 

@@ -3,6 +3,7 @@ pair and enqueue the CUDA kernels on the current torch stream.  No allocation, n
 fallback on the step path: if the CUDA library is absent ``_lib.load()`` raises.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -315,5 +316,6 @@ def fma_peak(device, dtype=torch.float64, iters=4096, blocks_per_sm=8):
         _lib.check(lib.rbs_fma_probe(code, n_threads, iters, _ptr(sink), stream))
         t1.record()
         t1.synchronize()
-        best = max(best, 2.0 * 8 * n_threads * iters / (t0.elapsed_time(t1) * 1e-3))
+        chains = 16 if os.environ.get("RBS_PROBE_MODE") == "2" else 8
+        best = max(best, 2.0 * chains * n_threads * iters / (t0.elapsed_time(t1) * 1e-3))
     return best
