@@ -769,3 +769,47 @@ def test_run_statistics_kernel(rb):
     ref = 0.5 * m * (qv[:, :3] ** 2).sum() + 0.5 * I * (qv[:, 3:] ** 2).sum() + m * 9.8 * qp[:, 2].sum()
     assert got[3] == pytest.approx(ref, rel=1e-10) and got[4] == pytest.approx(qp[:, 2].max(), rel=1e-14)
     assert got[1] == data.counters()[0].sum()
+
+
+def test_host_buffer_drivers_two_ball_and_multi_sphere(rb):
+    """rbs_run_two_ball_host / rbs_run_multi_sphere_host: reference-layout host arrays in and out == device path."""
+    from rigidbody_simulation_b200 import stepper, synth
+    from rigidbody_simulation_b200.src.simulation import ball_collision, multi_sphere_bounce as ms
+    E = 30_000
+    s = synth.two_ball(E)
+    model, data = ball_collision.build(E)
+    data.set_state(s["qpos"], s["qvel"])
+    stepper.step_two_ball(model, data, 0.01, 1.0, 0.3, radius=0.1, substeps=130)
+    qp_h, qv_h = s["qpos"].copy(), s["qvel"].copy()
+    stepper.run_two_ball_host(model, qp_h, qv_h, 130, dt=0.01, restitution=1.0, friction=0.3, radius=0.1, substeps=50)
+    gq, gv = state_of(data)
+    assert (qp_h == gq).all() and (qv_h == gv).all()
+    E, B = 700, 27
+    s = synth.multi_sphere(E, n_body=B, friction=0.2)
+    model, data = ms.build(E, n_body=B)
+    data.set_state(s["qpos"], s["qvel"])
+    stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.2, substeps=45)
+    qp_h, qv_h = s["qpos"].copy(), s["qvel"].copy()
+    stepper.run_multi_sphere_host(model, qp_h, qv_h, 45, dt=0.01, restitution=1.0, friction=0.2, substeps=8)
+    gq, gv = state_of(data)
+    assert (qp_h == gq).all() and (qv_h == gv).all()
+    with pytest.raises(ValueError):                       # wrong shape is refused before anything is launched
+        stepper.run_multi_sphere_host(model, qp_h[:, :-1].copy(), qv_h, 1)
+
+
+def test_free_functions_follow_input_precision(rb):
+    """float32 CUDA tensors select the float kernels (and match the float oracle bit for bit); float64 the double ones."""
+    rng = np.random.default_rng(9)
+    n = 1000
+    v, w, r = rng.uniform(-2, 2, (n, 3)), rng.uniform(-5, 5, (n, 3)), rng.uniform(-0.3, 0.3, (n, 3))
+    nn = rng.normal(size=(n, 3))
+    nn /= np.linalg.norm(nn, axis=1, keepdims=True)
+    T32 = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")
+    jn, jt = rb.compute_collision_impulse_friction(2.5, None, T32(v), T32(w), T32(r), T32(nn), 0.8, 0.4)
+    assert jn.dtype == torch.float32 and jt.shape == (n, 3)
+    ojn, ojt = co.impulse_friction(np.full(n, 2.5), v, w, r, nn, np.full(n, 0.8), np.full(n, 0.4), dtype=np.float32)
+    assert (jn.cpu().numpy() == ojn).all() and (jt.cpu().numpy() == ojt).all()
+    Iw = rb.compute_inertia_tensor_world(T32(rng.uniform(0.1, 2, (n, 3))), T32(rng.normal(size=(n, 4))))
+    assert Iw.dtype == torch.float32 and Iw.shape == (n, 3, 3)
+    sym = (Iw - Iw.transpose(1, 2)).abs().max()
+    assert float(sym) < 1e-5
