@@ -43,7 +43,7 @@ for name, geom, gen, E in (("cfg2 sphere on incline", "sphere", lambda n: synth.
     size = [s["radius"]] if geom == "sphere" else s["half"]
     e = s["restitution"] if np.ndim(s["restitution"]) else np.full(E, s["restitution"])
     mu = s["friction"] if np.ndim(s["friction"]) else np.full(E, s["friction"])
-    for policy in ("strict", "strict+literal inertia", "fast"):
+    for policy in ("strict, isotropic shortcut", "strict (default: literal inertia)", "fast"):
         model = mj.MjModel.from_xml_string(scenes.single_body_xml(geom, size, plane_euler=(s.get("theta", 0.7), 0, 0)), nenv=E)
         model.set_per_env(restitution=e, friction=mu)
         data = mj.MjData(model)
@@ -80,12 +80,12 @@ for upto in CHECK:
     gq, gv = state_of(data)
     errs[upto] = max(comp_rel_err(gq, qp, 1e-3), comp_rel_err(gv, qv, 1e-3))
 mism = int(((data.n_contacts[:E].cpu().numpy() != hits[0]) | (data.n_impulses[:E].cpu().numpy() != hits[1])).sum())
-row("cfg3 two balls", "strict", errs, mism, E)
+row("cfg3 two balls", "strict (default)", errs, mism, E)
 
 # config 5 multi sphere ------------------------------------------------------------------------------------------
 E, B = 2000, 64
 s = synth.multi_sphere(E, n_body=B, friction=0.3)
-for policy in ("strict", "fast"):
+for policy in ("strict", "fast"):                       # strict = default = literal inertia
     model, data = multi_sphere_bounce.build(E, n_body=B)
     data.set_state(s["qpos"], s["qvel"])
     qp, qv = s["qpos"].reshape(E, B, 7).copy(), s["qvel"].reshape(E, B, 6).copy()
@@ -99,4 +99,4 @@ for policy in ("strict", "fast"):
         gq, gv = state_of(data)
         errs[upto] = max(comp_rel_err(gq.ravel(), qp.ravel(), 1e-3), comp_rel_err(gv.ravel(), qv.ravel(), 1e-3))
     calls, imps = data.counters()
-    row("cfg5 64 spheres (mu=0.3), horizon 100", policy, errs, int(((calls != cnt[0]).any(axis=1) | (imps != cnt[1]).any(axis=1)).sum()), E)
+    row("cfg5 64 spheres (mu=0.3), horizon 100", "strict (default: literal inertia)" if policy == "strict" else policy, errs, int(((calls != cnt[0]).any(axis=1) | (imps != cnt[1]).any(axis=1)).sum()), E)
