@@ -77,6 +77,8 @@ template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_a
     }
     p.dt = (T)a->dt;
     p.thr = (T)a->contact_threshold;
+    for (int i = 0; i < 3; ++i) p.gdt[i] = p.g[i] * p.dt;
+    p.hdt = (T)0.5 * p.dt;
     p.n_contacts = a->n_contacts ? a->n_contacts + w.off : nullptr;
     p.n_impulses = a->n_impulses ? a->n_impulses + w.off : nullptr;
     return p;
