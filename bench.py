@@ -174,7 +174,7 @@ def b200_arm(args):
         sample = synth.sphere_incline(cores * args.cpu_envs_per_core)
         cpu = cpu_baseline.python_port_sphere_incline(sample, cores, args.cpu_envs_per_core, args.cpu_steps)
         try:
-            cpu_native = cpu_baseline.c_port_sphere_incline(synth.sphere_incline(1 << 16), steps=200)
+            cpu_native = cpu_baseline.c_port_sphere_incline(synth.sphere_incline(1 << 16), steps=200, threads=cores)
         except Exception as exc:                              # the native port is informative only
             cpu_native = {"error": str(exc)}
 
