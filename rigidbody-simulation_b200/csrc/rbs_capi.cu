@@ -592,22 +592,34 @@ int rbs_run_body_plane_host(const rbs_body_plane_args *a, void *qpos_host, void 
     rc = workspace((size_t)E * 26 * es, &base);
     if (rc) return rc;
     char *qpos_d = static_cast<char *>(base), *qvel_d = qpos_d + (size_t)E * 7 * es, *state_d = qvel_d + (size_t)E * 6 * es;
-    // chunk = a whole number of full waves of CTAs, so that no chunk ends in a ragged partial wave
-    long chunk = (E + kMaxChunks - 1) / kMaxChunks;
+    // Chunks are whole numbers of CTA waves (no chunk ends in a ragged partial wave).  Only the first copy-in and the
+    // last copy-out are exposed, so the first and the last chunk are one wave quantum; the ones in between share the rest.
     const long quantum = (long)g_pipe.sm_count * 4 * rbs::kBlock;
-    chunk = ((chunk + quantum - 1) / quantum) * quantum;
-    const int n_chunks = (int)((E + chunk - 1) / chunk);
+    long offs[kMaxChunks + 1];
+    int n_chunks = 0;
+    offs[0] = 0;
+    if (E <= 3 * quantum) {
+        offs[++n_chunks] = E;
+    } else {
+        offs[++n_chunks] = quantum;
+        const long middle = E - 2 * quantum;
+        const int n_mid = kMaxChunks - 2;
+        long per = (middle + n_mid - 1) / n_mid;
+        per = ((per + quantum - 1) / quantum) * quantum;
+        for (long done = 0; done < middle; done += per) offs[n_chunks + 1] = offs[n_chunks] + (middle - done < per ? middle - done : per), ++n_chunks;
+        offs[n_chunks + 1] = E, ++n_chunks;
+    }
     cudaStream_t user = as_stream(a->stream);
     RBS_CUDA(cudaEventRecord(g_pipe.start, user));
     RBS_CUDA(cudaStreamWaitEvent(g_pipe.in, g_pipe.start, 0));
     for (int c = 0; c < n_chunks; ++c) {
-        const long off = c * chunk, cnt = (E - off < chunk) ? E - off : chunk;
+        const long off = offs[c], cnt = offs[c + 1] - offs[c];
         RBS_CUDA(cudaMemcpyAsync(qpos_d + off * 7 * es, (char *)qpos_host + off * 7 * es, cnt * 7 * es, cudaMemcpyHostToDevice, g_pipe.in));
         RBS_CUDA(cudaMemcpyAsync(qvel_d + off * 6 * es, (char *)qvel_host + off * 6 * es, cnt * 6 * es, cudaMemcpyHostToDevice, g_pipe.in));
         RBS_CUDA(cudaEventRecord(g_pipe.arrived[c], g_pipe.in));
     }
     for (int c = 0; c < n_chunks; ++c) {
-        const long off = c * chunk, cnt = (E - off < chunk) ? E - off : chunk;
+        const long off = offs[c], cnt = offs[c + 1] - offs[c];
         cudaStream_t cs = g_pipe.compute[c & 1];
         char *state_c = state_d + off * 13 * es;
         RBS_CUDA(cudaStreamWaitEvent(cs, g_pipe.arrived[c], 0));
