@@ -813,3 +813,32 @@ def test_free_functions_follow_input_precision(rb):
     assert Iw.dtype == torch.float32 and Iw.shape == (n, 3, 3)
     sym = (Iw - Iw.transpose(1, 2)).abs().max()
     assert float(sym) < 1e-5
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_contact_threshold_semantics(rb, arith):
+    """contacts with |dist| < contact_threshold are skipped (collision.py:79-80): the fast kernel folds
+    `dist < 0 and not |dist| < thr` into one comparison -- same decisions as the oracle, including thr = exactly |dist|."""
+    from rigidbody_simulation_b200 import stepper, synth
+    E = 60_000
+    s = synth.sphere_incline(E)
+    for thr in (1e-3, 5e-2):
+        model, data = make_single(rb, "sphere", [0.2], 0.7, s["qpos"], s["qvel"])
+        model.set_per_env(restitution=s["restitution"], friction=s["friction"])
+        qp, qv = s["qpos"].copy(), s["qvel"].copy()
+        cnt = (np.zeros(E, np.uint32), np.zeros(E, np.uint32))
+        co.step_body_plane(qp, qv, 250, geom="sphere", mass=model.body_mass[-1], inertia=model.body_inertia[-1], size=0.2,
+                           plane_pos=[0, 0, 0], plane_normal=model.plane_normal, gravity=G, dt=s["dt"],
+                           restitution=s["restitution"], friction=s["friction"], threshold=thr, counters=cnt)
+        stepper.step_body_plane(model, data, -1, s["dt"], None, None, thr, substeps=250, arith=arith)
+        calls, imps = data.counters()
+        assert cnt[0].sum() > E
+        assert (calls[:, 0] == cnt[0]).all() and (imps[:, 0] == cnt[1]).all(), thr
+    # a sphere resting exactly thr deep: |dist| == thr is NOT below the threshold, so the contact is processed
+    qpos = np.array([[0.0, 0.0, 0.2 - 0.015625, 1, 0, 0, 0]])          # dist = -2^-6 exactly
+    model, data = make_single(rb, "sphere", [0.2], 0.0, qpos, np.zeros((1, 6)))
+    stepper.step_body_plane(model, data, -1, 0.009, 1.0, 0.5, 0.015625, substeps=1, arith=arith)
+    assert int(data.counters()[0].sum()) == 1
+    model, data = make_single(rb, "sphere", [0.2], 0.0, qpos, np.zeros((1, 6)))
+    stepper.step_body_plane(model, data, -1, 0.009, 1.0, 0.5, 0.015626, substeps=1, arith=arith)
+    assert int(data.counters()[0].sum()) == 0
