@@ -324,7 +324,8 @@ def b200_arm(args):
                          "traffic": 194.2e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
             "roofline_k1": {"bound": "hbm", "kernel": "same kernel, 1 substep per launch (the reference's per-frame call)",
                             "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
-                            "peak_source": hbm_src, "bytes_per_env": (26 + 2) * esize, "launch_ms": k1_launch_ms,
+                            "peak_source": hbm_src, "frac_of_nominal_8TBps": k1_gbs / 8000.0,
+                            "bytes_per_env": (26 + 2) * esize, "launch_ms": k1_launch_ms,
                             "env_steps_per_s": world * E / (k1_launch_ms * 1e-3),
                             "traffic": 185.9e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
         }

@@ -34,6 +34,71 @@ def _worker(job):
     return qpos.shape[0] * steps, time.perf_counter() - t0
 
 
+def _worker_config(job):
+    """Generic worker: kind in {'cube', 'two_ball', 'multi_sphere'}; returns (env_steps, seconds)."""
+    import pyport
+    kind, qpos, qvel, extra, steps = job
+    mj = pyport.fake_mujoco()
+    t0 = time.perf_counter()
+    if kind == "cube":
+        model = mj.MjModel.from_xml_string(pyport.single_body_xml("box", [0.4, 0.4, 0.4], plane_euler=(extra["theta"], 0, 0)))
+        for i in range(qpos.shape[0]):
+            data = mj.MjData(model)
+            data.qpos[:], data.qvel[:] = qpos[i], qvel[i]
+            for _ in range(steps):      # cube_incline.py:75-77: dt, restitution, friction passed; threshold left at 1e-4
+                pyport.step_scheme_a(model, "obj", data, dt=0.009, restitution=0.2, friction_coeff=0.6, contact_threshold=1e-4)
+    elif kind == "two_ball":
+        model = mj.MjModel.from_xml_string(pyport.multi_sphere_xml(2))
+        m = float(model.body_mass[1])
+        iinv = np.eye(3) / (0.4 * m * 0.01)
+        g = np.array([0.0, 0.0, -9.8])
+        for i in range(qpos.shape[0]):
+            data = mj.MjData(model)
+            data.qpos[:], data.qvel[:] = qpos[i], qvel[i]
+            for _ in range(steps):
+                mj.mj_forward(model, data)                       # ball_collision.py:74 (the reference calls it too)
+                pyport.step_two_ball(data, (m, m), (iinv, iinv), g, 0.01, 1.0, 0.3, 0.1)
+    else:
+        B = extra["n_body"]
+        model = mj.MjModel.from_xml_string(pyport.multi_sphere_xml(B))
+        for i in range(qpos.shape[0]):
+            data = mj.MjData(model)
+            data.qpos[:], data.qvel[:] = qpos[i], qvel[i]
+            for _ in range(steps):
+                pyport.step_multi_sphere(model, data, 0.01, 1.0, extra["friction"])
+    return qpos.shape[0] * steps, time.perf_counter() - t0
+
+
+def python_port_config(kind, sample, cores=None, envs_per_core=4, steps=100, extra=None):
+    """Aggregate env-steps/s of the Python port for another BASELINE config (cube / two_ball / multi_sphere)."""
+    import multiprocessing as mp
+    _require_importable_main()
+    cores = cores or os.cpu_count() or 1
+    n = cores * envs_per_core
+    jobs = [(kind, sample["qpos"][c * envs_per_core:(c + 1) * envs_per_core].copy(),
+             sample["qvel"][c * envs_per_core:(c + 1) * envs_per_core].copy(), extra or {}, steps) for c in range(cores)]
+    for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.setdefault(var, "1")
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_warm, range(cores), chunksize=1)
+        t0 = time.perf_counter()
+        res = pool.map(_worker_config, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    env_steps = sum(r[0] for r in res)
+    return {"value": env_steps / wall, "unit": "env-substeps/s", "cores": cores, "kind": "port",
+            "sample": f"{n} envs x {steps} steps, Python/NumPy port under the fake MuJoCo, {cores} processes, wall {wall:.2f} s"}
+
+
+def _require_importable_main():
+    """The pools use the spawn start method: the parent's __main__ must be a real file (not stdin / -c), otherwise every
+    worker dies on start-up and the pool respawns them forever."""
+    main = sys.modules.get("__main__")
+    path = getattr(main, "__file__", None)
+    if path is None or not os.path.isfile(path):
+        raise RuntimeError("cpu_baseline needs to be driven from a script file (multiprocessing 'spawn')")
+
+
 def _warm(_):
     """Import everything and run a few steps so that interpreter start-up is outside the timed map."""
     import pyport
@@ -49,6 +114,7 @@ def python_port_sphere_incline(sample, cores=None, envs_per_core=16, steps=400):
     """``sample``: dict from synth.sphere_incline (at least cores*envs_per_core envs).  Returns a dict with the
     aggregate env-steps/s over ``cores`` worker processes (wall clock around the parallel map)."""
     import multiprocessing as mp
+    _require_importable_main()
     cores = cores or os.cpu_count() or 1
     n = cores * envs_per_core
     if sample["qpos"].shape[0] < n:
