@@ -219,3 +219,17 @@ def test_bench_reference_arm_json_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "env-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_missing_extension_fails_loudly():
+    """If librbsim_b200.so has not been built the package refuses to work -- it never computes some other way."""
+    code = ("import sys; sys.path.insert(0, '.');"
+            "import rigidbody_simulation_b200 as rb;"
+            "rb._lib.LIB_PATH = rb._lib.LIB_PATH + '.absent'; rb._lib._lib = None\n"
+            "try:\n    rb._lib.load()\nexcept rb.RbsError as e:\n    print('raised', 'no CPU fallback' in str(e).lower() or 'fallback' in str(e))\n"
+            "import numpy as np\n"
+            "try:\n    rb.compute_inverse_inertia(1.0, 0.1); rb.compute_collision_impulse(1.0, 2500.0, np.zeros(3), np.zeros(3), np.zeros(3), np.array([0,0,1.0]), 1.0, 0.3)\n"
+            "except rb.RbsError:\n    print('free function refused')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "raised True" in r.stdout and "free function refused" in r.stdout
