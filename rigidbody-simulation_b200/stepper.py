@@ -123,12 +123,40 @@ def body_plane_args(model, data, body_id, dt, restitution, friction_coeff, conta
     return a
 
 
+def _key_of(value):
+    """cache key of a scalar-or-per-env argument: tensors by storage address (they are kept alive by the cached struct)"""
+    if torch.is_tensor(value):
+        return ("t", value.data_ptr(), value.numel())
+    if isinstance(value, np.ndarray) and value.ndim > 0:
+        return None                                   # host arrays are uploaded on every call: not cacheable
+    return value
+
+
 def step_body_plane(model, data, body_id, dt, restitution, friction_coeff, contact_threshold,
                     scheme=RBS_SCHEME_A, substeps=1, count=True, strict_inertia=None, arith="strict", env_range=None):
     """arith: "strict" reproduces the reference's rounding sequence; "fast" re-associates for the FP pipe
-    (scheme A + isotropic inertia only; <= 1e-12 relative per step in fp64)."""
-    a = body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold, scheme, substeps,
-                        count, strict_inertia, arith, env_range)
+    (scheme A + isotropic inertia only; <= 1e-12 relative per step in fp64).
+
+    The marshalled argument struct is cached per call signature and per identity of every device buffer it points to,
+    so a per-frame loop pays for one ctypes call per step, not for rebuilding 30 fields."""
+    kr, kf = _key_of(restitution), _key_of(friction_coeff)
+    a = None
+    if not (kr is None and restitution is not None) and not (kf is None and friction_coeff is not None):
+        pe = model.per_env
+        key = (body_id, dt, kr, kf, contact_threshold, scheme, count, strict_inertia, arith, env_range, data.state.data_ptr(),
+               None if data.xfrc_applied is None else data.xfrc_applied.data_ptr(),
+               tuple((k, t.data_ptr()) for k, t in pe.items()))
+        cache = data.__dict__.setdefault("_args_cache", {})
+        a = cache.get(key)
+        if a is None:
+            if len(cache) > 64:
+                cache.clear()
+            a = cache[key] = body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold,
+                                             scheme, substeps, count, strict_inertia, arith, env_range)
+        a.substeps = int(substeps)
+    if a is None:
+        a = body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold, scheme, substeps,
+                            count, strict_inertia, arith, env_range)
     a.stream = current_stream(model.device)
     _lib.check(_lib.load().rbs_step_body_plane(ctypes.byref(a)))
 
