@@ -63,3 +63,36 @@ def test_argument_validation_needs_no_gpu():
     assert lib.rbs_impulse_friction(5, 1, None, 1.0, None, None, None, None, None, 1.0, None, 0.5, None, None, None, None) == _lib.RBS_EINVAL
     with pytest.raises(ValueError):
         _lib.check(_lib.RBS_EINVAL)
+
+
+def _build_c_client(tmp_path):
+    import subprocess
+    from rigidbody_simulation_b200 import _lib
+    exe = str(tmp_path / "cabi_client")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["/usr/bin/gcc", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cabi_client.c"),
+                    "-o", exe, "-L", libdir, "-lrbsim_b200", "-Wl,-rpath," + libdir], check=True)
+    return exe
+
+
+def test_plain_c_client_links_and_validates(tmp_path):
+    """A C program that includes only include/rbsim_b200.h links against the library and gets the documented
+    status codes (no GPU involved)."""
+    import subprocess
+    _lib_ok = test_library_exports_every_declared_symbol  # noqa: F841  (ensures the library is built)
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([exe, "validate"], capture_output=True, text=True)
+    assert r.returncode == 0 and "validate ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_plain_c_client_runs_config1(tmp_path, golden):
+    """configs[0] (single sphere from rest, 2000 steps) driven from C through rbs_run_body_plane_host."""
+    import subprocess
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([exe, "sphere"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    vals = [float(x) for x in r.stdout.split()]
+    assert vals[0] == 0.0 and vals[1] == 0.0 and vals[3:7] == [1.0, 0.0, 0.0, 0.0]
+    assert vals[2] == pytest.approx(0.20844281676054977, rel=1e-12)       # SURVEY Appendix B, from-rest variant
+    assert vals[7] == pytest.approx(0.1051418877747299, rel=1e-11)
