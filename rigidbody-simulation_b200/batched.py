@@ -206,6 +206,24 @@ class BatchedData:
         x = torch.as_tensor(xfrc, dtype=self.dtype).to(self.device).reshape(self.nenv, 6)
         self.xfrc_applied = x.t().contiguous()
 
+    def state_dict(self):
+        """Checkpoint: the SoA state, the event counters, the applied wrench and the (never advanced) time.
+        The reference has no checkpointing (only mj_resetData); resuming from this is bit-exact because the
+        steppers keep no hidden state between launches."""
+        return {"layout": self.layout, "state": self.state.detach().cpu().clone(), "n_contacts": self.n_contacts.cpu().clone(),
+                "n_impulses": self.n_impulses.cpu().clone(), "time": self.time,
+                "xfrc_applied": None if self.xfrc_applied is None else self.xfrc_applied.cpu().clone()}
+
+    def load_state_dict(self, sd):
+        if sd["layout"] != self.layout or tuple(sd["state"].shape) != tuple(self.state.shape):
+            raise ValueError("checkpoint does not match this scene (layout / shape)")
+        self.state.copy_(sd["state"].to(self.dtype))
+        self.n_contacts.copy_(sd["n_contacts"])
+        self.n_impulses.copy_(sd["n_impulses"])
+        self.time = float(sd["time"])
+        x = sd.get("xfrc_applied")
+        self.xfrc_applied = None if x is None else x.to(device=self.device, dtype=self.dtype).contiguous()
+
     def counters(self):
         """(contacts handed to the impulse routine, impulses applied) per body, as int64 host arrays."""
         return (self.n_contacts.cpu().numpy().astype(np.int64).reshape(self.nenv, self.nfree),

@@ -842,3 +842,20 @@ def test_contact_threshold_semantics(rb, arith):
     model, data = make_single(rb, "sphere", [0.2], 0.0, qpos, np.zeros((1, 6)))
     stepper.step_body_plane(model, data, -1, 0.009, 1.0, 0.5, 0.015626, substeps=1, arith=arith)
     assert int(data.counters()[0].sum()) == 0
+
+
+def test_checkpoint_resume_is_bit_exact(rb):
+    """Stop after 70 substeps, checkpoint, resume in a fresh object: same bits as the uninterrupted run."""
+    from rigidbody_simulation_b200 import stepper, synth
+    E = 20_000
+    s = synth.cube(E, kind="bounce")
+    kw = dict(dt=0.009, restitution=0.2, friction_coeff=0.6, contact_threshold=1e-4)
+    model, straight = make_single(rb, "box", s["half"], 0.0, s["qpos"], s["qvel"])
+    stepper.step_body_plane(model, straight, -1, substeps=150, **kw)
+    model, first = make_single(rb, "box", s["half"], 0.0, s["qpos"], s["qvel"])
+    stepper.step_body_plane(model, first, -1, substeps=70, **kw)
+    sd = first.state_dict()
+    model, second = make_single(rb, "box", s["half"], 0.0, np.zeros_like(s["qpos"]) + [0, 0, 9, 1, 0, 0, 0], np.zeros_like(s["qvel"]))
+    second.load_state_dict(sd)
+    stepper.step_body_plane(model, second, -1, substeps=80, **kw)
+    assert torch.equal(second.state, straight.state) and torch.equal(second.n_contacts, straight.n_contacts)

@@ -233,3 +233,20 @@ def test_missing_extension_fails_loudly():
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "raised True" in r.stdout and "free function refused" in r.stdout
+
+
+def test_checkpoint_round_trip_cpu(tmp_path):
+    import torch
+    import rigidbody_simulation_b200 as rb
+    from rigidbody_simulation_b200 import scenes
+    m = rb.BatchedModel.from_xml_path(scenes.model_path("ball_collision"), nenv=6, device="cpu")
+    d = rb.BatchedData(m)
+    d.set_state(np.random.default_rng(0).normal(size=(6, 14)), np.random.default_rng(1).normal(size=(6, 12)))
+    d.n_contacts += 3
+    torch.save(d.state_dict(), tmp_path / "ckpt.pt")
+    d2 = rb.BatchedData(m)
+    d2.load_state_dict(torch.load(tmp_path / "ckpt.pt"))
+    assert torch.equal(d2.state, d.state) and torch.equal(d2.n_contacts, d.n_contacts)
+    m3 = rb.BatchedModel.from_xml_path(scenes.model_path("sphere"), nenv=6, device="cpu")
+    with pytest.raises(ValueError):
+        rb.BatchedData(m3).load_state_dict(d.state_dict())
