@@ -262,7 +262,7 @@ template <typename T> void launch_multi_sphere(const rbs_multi_sphere_args *a) {
     const int epb = threads / B;
     const rbs::MultiSphereParams<T> p = make_params<T>(a, epb);
     const unsigned grid = (unsigned)((a->n_env + epb - 1) / epb);
-    const size_t smem = (size_t)epb * B * 4 * sizeof(T);
+    const size_t smem = (size_t)epb * B * 4 * sizeof(T) + (size_t)epb * B * sizeof(float4);   // centres + fp32 relative copies
     cudaStream_t st = as_stream(a->stream);
     const bool iso = a->inertia_mode == RBS_INERTIA_ISOTROPIC;
     if (a->arith == RBS_ARITH_FAST) {
