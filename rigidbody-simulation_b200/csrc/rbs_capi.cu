@@ -79,6 +79,38 @@ template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_a
     p.thr = (T)a->contact_threshold;
     for (int i = 0; i < 3; ++i) p.gdt[i] = p.g[i] * p.dt;
     p.hdt = (T)0.5 * p.dt;
+    {   // plane frame (double on the host): rows t1, t2, n; quaternion of that rotation; gravity*dt in the frame
+        const double n[3] = {a->plane_normal[0], a->plane_normal[1], a->plane_normal[2]};
+        double t1[3] = {0, 0, 0}, t2[3];
+        const int ax = fabs(n[0]) < 0.9 ? 0 : 1;
+        t1[ax] = 1.0;
+        const double d = n[ax];
+        double len = 0.0;
+        for (int i = 0; i < 3; ++i) { t1[i] -= d * n[i]; len += t1[i] * t1[i]; }
+        len = sqrt(len);
+        for (int i = 0; i < 3; ++i) t1[i] /= len;
+        t2[0] = n[1] * t1[2] - n[2] * t1[1]; t2[1] = n[2] * t1[0] - n[0] * t1[2]; t2[2] = n[0] * t1[1] - n[1] * t1[0];
+        const double R[9] = {t1[0], t1[1], t1[2], t2[0], t2[1], t2[2], n[0], n[1], n[2]};
+        double q[4];
+        const double tr = R[0] + R[4] + R[8];
+        if (tr > 0) {
+            const double s4 = 2.0 * sqrt(tr + 1.0);
+            q[0] = 0.25 * s4; q[1] = (R[7] - R[5]) / s4; q[2] = (R[2] - R[6]) / s4; q[3] = (R[3] - R[1]) / s4;
+        } else if (R[0] > R[4] && R[0] > R[8]) {
+            const double s4 = 2.0 * sqrt(1.0 + R[0] - R[4] - R[8]);
+            q[0] = (R[7] - R[5]) / s4; q[1] = 0.25 * s4; q[2] = (R[1] + R[3]) / s4; q[3] = (R[2] + R[6]) / s4;
+        } else if (R[4] > R[8]) {
+            const double s4 = 2.0 * sqrt(1.0 + R[4] - R[0] - R[8]);
+            q[0] = (R[2] - R[6]) / s4; q[1] = (R[1] + R[3]) / s4; q[2] = 0.25 * s4; q[3] = (R[5] + R[7]) / s4;
+        } else {
+            const double s4 = 2.0 * sqrt(1.0 + R[8] - R[0] - R[4]);
+            q[0] = (R[3] - R[1]) / s4; q[1] = (R[2] + R[6]) / s4; q[2] = (R[5] + R[7]) / s4; q[3] = 0.25 * s4;
+        }
+        for (int i = 0; i < 9; ++i) p.frame[i] = (T)R[i];
+        for (int i = 0; i < 4; ++i) p.frame_q[i] = (T)q[i];
+        for (int i = 0; i < 3; ++i)
+            p.gdt_pf[i] = (T)((R[3 * i] * a->gravity[0] + R[3 * i + 1] * a->gravity[1] + R[3 * i + 2] * a->gravity[2]) * a->dt);
+    }
     p.n_contacts = a->n_contacts ? a->n_contacts + w.off : nullptr;
     p.n_impulses = a->n_impulses ? a->n_impulses + w.off : nullptr;
     return p;
@@ -119,6 +151,11 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
     cudaStream_t st = w.stream;
     if (a->xfrc) {
         rbs::step_sphere_plane_fast_kernel<T, 4, true><<<grid, rbs::kBlock, 0, st>>>(p);
+        return;
+    }
+    static const int pf_min = [] { const char *e = getenv("RBS_PF_MIN_SUBSTEPS"); return e ? atoi(e) : 4; }();
+    if (a->substeps >= pf_min) {        // fused launches: work in the plane frame (two rotations per launch pay off)
+        rbs::step_sphere_plane_pf_kernel<T, 6><<<grid, rbs::kBlock, 0, st>>>(p);
         return;
     }
     switch (tuning_minb(a->substeps, RBS_ARITH_FAST)) {
