@@ -155,7 +155,12 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
     }
     static const int pf_min = [] { const char *e = getenv("RBS_PF_MIN_SUBSTEPS"); return e ? atoi(e) : 4; }();
     if (a->substeps >= pf_min) {        // fused launches: work in the plane frame (two rotations per launch pay off)
-        rbs::step_sphere_plane_pf_kernel<T, 6><<<grid, rbs::kBlock, 0, st>>>(p);
+        switch (tuning_minb(a->substeps, RBS_ARITH_FAST)) {
+            case 4: rbs::step_sphere_plane_pf_kernel<T, 4><<<grid, rbs::kBlock, 0, st>>>(p); break;
+            case 5: rbs::step_sphere_plane_pf_kernel<T, 5><<<grid, rbs::kBlock, 0, st>>>(p); break;
+            case 8: rbs::step_sphere_plane_pf_kernel<T, 8><<<grid, rbs::kBlock, 0, st>>>(p); break;
+            default: rbs::step_sphere_plane_pf_kernel<T, 6><<<grid, rbs::kBlock, 0, st>>>(p); break;
+        }
         return;
     }
     switch (tuning_minb(a->substeps, RBS_ARITH_FAST)) {
