@@ -36,8 +36,9 @@ def parse():
     p.add_argument("--arith", default="fast", choices=["strict", "fast"],
                    help="strict = the reference's rounding sequence; fast = FMA/reciprocal re-association (<=1e-12/step)")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--cpu-envs-per-core", type=int, default=16)
-    p.add_argument("--cpu-steps", type=int, default=400)
+    p.add_argument("--cpu-envs-per-core", type=int, default=64,
+                   help="CPU baseline sample: environments per host core (64 x 2048 steps is ~12 s per core)")
+    p.add_argument("--cpu-steps", type=int, default=2048, help="CPU baseline sample: steps per environment (= one bench step)")
     p.add_argument("--k1-launches", type=int, default=64, help="launches per step of the 1-substep-per-launch regime")
     return p.parse_args()
 

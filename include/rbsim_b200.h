@@ -163,7 +163,9 @@ typedef struct rbs_multi_sphere_args {
     int n_body;                /* 1 .. 1024 */
     int inertia_mode;
     int arith;                 /* RBS_ARITH_FAST needs RBS_INERTIA_ISOTROPIC (spheres: always valid) */
-    int reserved;
+    int list_skin_percent;     /* partner-list skin in % of the radius: 0 = adaptive per CTA (starts at 50, or at
+                                  RBS_MS_SKIN_PERCENT; launches of < 4 substeps scan instead); > 0 = pinned; < 0 = no skin (all partners are scanned every
+                                  substep).  A tuning knob: results never depend on it. */
     long n_env;
     long stride;               /* >= n_env * n_body */
     void *state;               /* [13][stride], body-fastest */

@@ -59,7 +59,7 @@ class MultiSphereArgs(Structure):
     """struct rbs_multi_sphere_args"""
     _fields_ = [
         ("dtype", c_int), ("substeps", c_int), ("n_body", c_int), ("inertia_mode", c_int),
-        ("arith", c_int), ("reserved", c_int),
+        ("arith", c_int), ("list_skin_percent", c_int),
         ("n_env", c_long), ("stride", c_long),
         ("state", c_void_p),
         ("mass", c_void_p), ("mass_u", c_double),

@@ -273,6 +273,13 @@ template <typename T> rbs::MultiSphereParams<T> make_params(const rbs_multi_sphe
     p.dt = (T)a->dt;
     p.rest = (T)a->restitution;
     p.fric = (T)a->friction;
+    // 0 = adaptive per CTA, starting at 50 % (or at RBS_MS_SKIN_PERCENT); > 0 = pinned; < 0 = no lists.  A launch of
+    // fewer than 4 substeps (the reference's per-frame call) cannot amortise a list and scans every substep.
+    static const int default_skin = [] { const char *e = getenv("RBS_MS_SKIN_PERCENT"); const int v = e ? atoi(e) : 50; return v > 0 ? v : 50; }();
+    int skin_pct = a->list_skin_percent != 0 ? a->list_skin_percent : default_skin;
+    if (a->list_skin_percent == 0 && a->substeps < 4) skin_pct = -1;
+    p.skin = skin_pct > 0 ? (T)(skin_pct * 0.01) : T(0);
+    p.skin_adapt = a->list_skin_percent == 0 && skin_pct > 0;
     p.n_contacts = a->n_contacts;
     p.n_impulses = a->n_impulses;
     return p;
@@ -304,25 +311,37 @@ template <typename T> void launch_multi_sphere(const rbs_multi_sphere_args *a) {
     const int epb = threads / B;
     const rbs::MultiSphereParams<T> p = make_params<T>(a, epb);
     const unsigned grid = (unsigned)((a->n_env + epb - 1) / epb);
-    const size_t smem = (size_t)epb * B * 4 * sizeof(T) + (size_t)epb * B * sizeof(float4);   // centres + fp32 relative copies
+    // centres + fp32 relative copies + partner lists (ceil(B/64) words per thread, word-major)
+    const size_t smem = (size_t)epb * B * 4 * sizeof(T) + (size_t)epb * B * sizeof(float4) +
+                        (size_t)((B + 63) / 64) * threads * sizeof(unsigned long long);
     cudaStream_t st = as_stream(a->stream);
     const bool iso = a->inertia_mode == RBS_INERTIA_ISOTROPIC;
+    // above 48 KB (B > ~450) the dynamic shared memory needs the opt-in attribute; set it once per instantiation
+#define RBS_MS_LAUNCH(KERNEL)                                                                                   \
+    do {                                                                                                        \
+        static size_t allowed = 48 * 1024;                                                                      \
+        if (smem > allowed) {                                                                                   \
+            if (cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) allowed = smem; \
+        }                                                                                                       \
+        KERNEL<<<grid, threads, smem, st>>>(p);                                                                 \
+    } while (0)
     if (a->arith == RBS_ARITH_FAST) {
-        if (threads <= 256) rbs::step_multi_sphere_fast_kernel<T, 256><<<grid, threads, smem, st>>>(p);
-        else if (threads <= 512) rbs::step_multi_sphere_fast_kernel<T, 512><<<grid, threads, smem, st>>>(p);
-        else rbs::step_multi_sphere_fast_kernel<T, 1024><<<grid, threads, smem, st>>>(p);
+        if (threads <= 256) RBS_MS_LAUNCH((rbs::step_multi_sphere_fast_kernel<T, 256>));
+        else if (threads <= 512) RBS_MS_LAUNCH((rbs::step_multi_sphere_fast_kernel<T, 512>));
+        else RBS_MS_LAUNCH((rbs::step_multi_sphere_fast_kernel<T, 1024>));
         return;
     }
     if (threads <= 256) {
-        if (iso) rbs::step_multi_sphere_kernel<T, 1, 256><<<grid, threads, smem, st>>>(p);
-        else rbs::step_multi_sphere_kernel<T, 0, 256><<<grid, threads, smem, st>>>(p);
+        if (iso) RBS_MS_LAUNCH((rbs::step_multi_sphere_kernel<T, 1, 256>));
+        else RBS_MS_LAUNCH((rbs::step_multi_sphere_kernel<T, 0, 256>));
     } else if (threads <= 512) {
-        if (iso) rbs::step_multi_sphere_kernel<T, 1, 512><<<grid, threads, smem, st>>>(p);
-        else rbs::step_multi_sphere_kernel<T, 0, 512><<<grid, threads, smem, st>>>(p);
+        if (iso) RBS_MS_LAUNCH((rbs::step_multi_sphere_kernel<T, 1, 512>));
+        else RBS_MS_LAUNCH((rbs::step_multi_sphere_kernel<T, 0, 512>));
     } else {
-        if (iso) rbs::step_multi_sphere_kernel<T, 1, 1024><<<grid, threads, smem, st>>>(p);
-        else rbs::step_multi_sphere_kernel<T, 0, 1024><<<grid, threads, smem, st>>>(p);
+        if (iso) RBS_MS_LAUNCH((rbs::step_multi_sphere_kernel<T, 1, 1024>));
+        else RBS_MS_LAUNCH((rbs::step_multi_sphere_kernel<T, 0, 1024>));
     }
+#undef RBS_MS_LAUNCH
 }
 
 // cached device workspace of the host-buffer drivers -------------------------------------------

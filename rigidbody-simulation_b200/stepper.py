@@ -219,7 +219,8 @@ def step_two_ball(model, data, dt, restitution, friction, radius=0.1, substeps=1
     _lib.check(_lib.load().rbs_step_two_ball(ctypes.byref(a)))
 
 
-def multi_sphere_args(model, data, dt, restitution, friction, substeps, count=True, strict_inertia=None, arith="strict"):
+def multi_sphere_args(model, data, dt, restitution, friction, substeps, count=True, strict_inertia=None, arith="strict",
+                      list_skin_percent=0):
     _require_cuda(model)
     if data.layout != "body":
         raise ValueError("the multi-sphere step needs BatchedData(model, layout='body')")
@@ -243,6 +244,7 @@ def multi_sphere_args(model, data, dt, restitution, friction, substeps, count=Tr
         pe.setdefault("inertia", I.t().repeat(1, E).contiguous())
     a = MultiSphereArgs()
     a.dtype, a.substeps, a.n_body = rbs_dtype(model.dtype), int(substeps), data.nfree
+    a.list_skin_percent = int(list_skin_percent)
     a.n_env, a.stride = data.nenv, data.stride
     a.state = _ptr(data.state)
     a.mass, a.mass_u = _ptr(pe.get("mass")), float(model.body_mass[first])
@@ -262,8 +264,11 @@ def multi_sphere_args(model, data, dt, restitution, friction, substeps, count=Tr
     return a
 
 
-def step_multi_sphere(model, data, dt, restitution, friction, substeps=1, count=True, strict_inertia=None, arith="strict"):
-    a = multi_sphere_args(model, data, dt, restitution, friction, substeps, count, strict_inertia, arith)
+def step_multi_sphere(model, data, dt, restitution, friction, substeps=1, count=True, strict_inertia=None, arith="strict",
+                      list_skin_percent=0):
+    """``list_skin_percent``: partner-list skin in % of the radius (0 = library default, < 0 = scan all partners every
+    substep); a tuning knob only, results do not depend on it."""
+    a = multi_sphere_args(model, data, dt, restitution, friction, substeps, count, strict_inertia, arith, list_skin_percent)
     a.stream = current_stream(model.device)
     _lib.check(_lib.load().rbs_step_multi_sphere(ctypes.byref(a)))
 

@@ -657,6 +657,35 @@ def test_multi_sphere_ragged_and_maximum_body_counts(rb):
         assert (calls == cnt[0]).all() and (imps == cnt[1]).all(), B
 
 
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_multi_sphere_partner_lists_never_change_results(rb, arith):
+    """The Verlet partner lists (PartnerLists in rbs_kernels.cuh) are a conservative superset of the contacts: every
+    skin -- none (all partners scanned every substep), 5 %, the default 50 %, 400 % -- gives bit-identical states and
+    event counts, for one-word (B = 64) and multi-word (B = 150) lists, uniform and per-body radii, fp64 and fp32."""
+    from rigidbody_simulation_b200 import stepper, synth
+    from rigidbody_simulation_b200.src.simulation import multi_sphere_bounce as ms
+    for B, E, dtype, per_body in ((64, 600, np.float64, False), (150, 40, np.float64, False), (64, 300, np.float32, False),
+                                  (27, 500, np.float64, True)):
+        s = synth.multi_sphere(E, n_body=B, friction=0.3)
+        results = []
+        for skin in (-1, 5, 0, 400):
+            model, data = ms.build(E, n_body=B, dtype=tdt(dtype))
+            if per_body:        # radii 0.08 .. 0.12 by body index; mass / inertia stay those of the XML
+                r = torch.tensor(0.08 + 0.04 * (np.arange(E * B) % B) / B, dtype=tdt(dtype), device="cuda")
+                model.set_per_env(radius=r, mass=torch.full_like(r, float(model.body_mass[1])),
+                                  inertia=torch.full((3, E * B), float(model.body_inertia[1][0]), dtype=tdt(dtype), device="cuda"))
+            data.set_state(s["qpos"], s["qvel"])
+            for k in (1, 7, 80):
+                stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.3, substeps=k, arith=arith, list_skin_percent=skin)
+            calls, imps = data.counters()
+            results.append((data.state.clone(), calls.copy(), imps.copy()))
+        for st, calls, imps in results[1:]:
+            assert torch.equal(st, results[0][0]), (B, dtype, per_body)
+            assert (calls == results[0][1]).all() and (imps == results[0][2]).all()
+        assert results[0][1].sum() > E * B          # pair and ground contacts are exercised
+        assert torch.isfinite(results[0][0]).all()
+
+
 def test_padded_stride_and_applied_wrench_per_env(rb):
     """stride > n_env (a window into a larger allocation) and a per-env applied wrench through the raw C ABI."""
     import ctypes
