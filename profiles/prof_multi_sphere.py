@@ -1,0 +1,28 @@
+"""ncu target: config 5 (64 spheres per env), fast policy, fp64.  Four launches of 128 substeps bring the scene to its
+steady regime; the fifth launch is the one to capture:
+    ncu --set full --clock-control none --import-source on -k regex:step_multi_sphere_fast -s 4 -c 1 \
+        -o gpurun_out/prof_ms python profiles/prof_multi_sphere.py
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+from rigidbody_simulation_b200 import stepper, synth
+from rigidbody_simulation_b200.src.simulation import multi_sphere_bounce
+
+E = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+s = synth.multi_sphere(E, n_body=64, friction=0.0)
+model, data = multi_sphere_bounce.build(E, device=torch.device("cuda:0"), dtype=torch.float64, n_body=64)
+data.set_state(s["qpos"], s["qvel"])
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+for i in range(5):
+    ev[i].record()
+    stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.0, substeps=128, count=(i == 4), arith="fast")
+ev[5].record()
+torch.cuda.synchronize()
+print("launch ms:", [round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(5)])
+calls, imps = data.counters()
+print("contacts / impulses per body-substep in the last launch:", calls.sum() / (E * 64 * 128), imps.sum() / (E * 64 * 128))

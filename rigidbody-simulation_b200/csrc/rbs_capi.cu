@@ -82,13 +82,22 @@ template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_a
     {   // plane frame (double on the host): rows t1, t2, n; quaternion of that rotation; gravity*dt in the frame
         const double n[3] = {a->plane_normal[0], a->plane_normal[1], a->plane_normal[2]};
         double t1[3] = {0, 0, 0}, t2[3];
-        const int ax = fabs(n[0]) < 0.9 ? 0 : 1;
-        t1[ax] = 1.0;
-        const double d = n[ax];
-        double len = 0.0;
-        for (int i = 0; i < 3; ++i) { t1[i] -= d * n[i]; len += t1[i] * t1[i]; }
-        len = sqrt(len);
-        for (int i = 0; i < 3; ++i) t1[i] /= len;
+        // x' along n x g: gravity then has no x' component and the plane-frame kernel adds two components per substep
+        const double *g = a->gravity;
+        const double c[3] = {n[1] * g[2] - n[2] * g[1], n[2] * g[0] - n[0] * g[2], n[0] * g[1] - n[1] * g[0]};
+        const double clen = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+        const double glen = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+        if (clen > 1e-9 * glen) {
+            for (int i = 0; i < 3; ++i) t1[i] = c[i] / clen;
+        } else {                            // g parallel to n (flat ground) or g = 0: any tangent will do
+            const int ax = fabs(n[0]) < 0.9 ? 0 : 1;
+            t1[ax] = 1.0;
+            const double d = n[ax];
+            double len = 0.0;
+            for (int i = 0; i < 3; ++i) { t1[i] -= d * n[i]; len += t1[i] * t1[i]; }
+            len = sqrt(len);
+            for (int i = 0; i < 3; ++i) t1[i] /= len;
+        }
         t2[0] = n[1] * t1[2] - n[2] * t1[1]; t2[1] = n[2] * t1[0] - n[0] * t1[2]; t2[2] = n[0] * t1[1] - n[1] * t1[0];
         const double R[9] = {t1[0], t1[1], t1[2], t2[0], t2[1], t2[2], n[0], n[1], n[2]};
         double q[4];
