@@ -164,12 +164,14 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
     }
     static const int pf_min = [] { const char *e = getenv("RBS_PF_MIN_SUBSTEPS"); return e ? atoi(e) : 4; }();
     if (a->substeps >= pf_min) {        // fused launches: work in the plane frame (two rotations per launch pay off)
-        switch (tuning_minb(a->substeps, RBS_ARITH_FAST)) {
-            case 4: rbs::step_sphere_plane_pf_kernel<T, 4><<<grid, rbs::kBlock, 0, st>>>(p); break;
-            case 5: rbs::step_sphere_plane_pf_kernel<T, 5><<<grid, rbs::kBlock, 0, st>>>(p); break;
-            case 8: rbs::step_sphere_plane_pf_kernel<T, 8><<<grid, rbs::kBlock, 0, st>>>(p); break;
-            default: rbs::step_sphere_plane_pf_kernel<T, 6><<<grid, rbs::kBlock, 0, st>>>(p); break;
-        }
+        const bool count = a->n_contacts || a->n_impulses, thr = a->contact_threshold > 0;
+        const bool wide = tuning_minb(a->substeps, RBS_ARITH_FAST) == 8;
+#define RBS_PF(MINB, COUNT, THR) rbs::step_sphere_plane_pf_kernel<T, MINB, COUNT, THR><<<grid, rbs::kBlock, 0, st>>>(p)
+#define RBS_PF_MINB(COUNT, THR) do { if (wide) RBS_PF(8, COUNT, THR); else RBS_PF(6, COUNT, THR); } while (0)
+        if (count) { if (thr) RBS_PF_MINB(true, true); else RBS_PF_MINB(true, false); }
+        else { if (thr) RBS_PF_MINB(false, true); else RBS_PF_MINB(false, false); }
+#undef RBS_PF_MINB
+#undef RBS_PF
         return;
     }
     switch (tuning_minb(a->substeps, RBS_ARITH_FAST)) {
