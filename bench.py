@@ -31,7 +31,7 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     p.add_argument("--substeps", type=int, default=2048, help="integration steps per bench step")
-    p.add_argument("--fuse", type=int, default=128, help="substeps fused per kernel launch")
+    p.add_argument("--fuse", type=int, default=256, help="substeps fused per kernel launch")
     p.add_argument("--dtype", default="fp64", choices=["fp64", "fp32"])
     p.add_argument("--arith", default="fast", choices=["strict", "fast"],
                    help="strict = the reference's rounding sequence; fast = FMA/reciprocal re-association (<=1e-12/step)")
@@ -313,7 +313,7 @@ def b200_arm(args):
                             "reference layout)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp64" if args.dtype == "fp64" else "fp32", "kernel": ("rbs::step_sphere_plane_pf_kernel<double,6> (plane-frame fast kernel)" if args.arith == "fast" else "rbs::step_body_plane_kernel<double,sphere,schemeA,iso>") if args.dtype == "fp64" else "float instantiation of the same kernel",
+            "roofline": {"bound": "fp64" if args.dtype == "fp64" else "fp32", "kernel": ("rbs::step_sphere_plane_pf_kernel<double,6,COUNT=false,THR=false> (plane-frame fast kernel)" if args.arith == "fast" else "rbs::step_body_plane_kernel<double,sphere,schemeA,iso>") if args.dtype == "fp64" else "float instantiation of the same kernel",
                          "achieved": fused_tflops, "peak": fp_peak, "unit": "TFLOP/s", "frac": fused_tflops / fp_peak,
                          "peak_source": "FMA microbenchmark rbs_fma_probe run in this process (MEASURED_PEAKS.json has no "
                                         "CUDA-core peak)",

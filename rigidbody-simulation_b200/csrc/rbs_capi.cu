@@ -322,8 +322,8 @@ template <typename T> void launch_multi_sphere(const rbs_multi_sphere_args *a) {
     const int epb = threads / B;
     const rbs::MultiSphereParams<T> p = make_params<T>(a, epb);
     const unsigned grid = (unsigned)((a->n_env + epb - 1) / epb);
-    // centres + fp32 relative copies + partner lists (ceil(B/64) words per thread, word-major)
-    const size_t smem = (size_t)epb * B * 4 * sizeof(T) + (size_t)epb * B * sizeof(float4) +
+    // two buffers of centres + fp32 relative copies + partner lists (ceil(B/64) words per thread, word-major)
+    const size_t smem = 2 * (size_t)epb * B * 4 * sizeof(T) + (size_t)epb * B * sizeof(float4) +
                         (size_t)((B + 63) / 64) * threads * sizeof(unsigned long long);
     cudaStream_t st = as_stream(a->stream);
     const bool iso = a->inertia_mode == RBS_INERTIA_ISOTROPIC;
