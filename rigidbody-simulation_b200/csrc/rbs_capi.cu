@@ -244,6 +244,8 @@ template <typename T> rbs::TwoBallParams<T> make_params(const rbs_two_ball_args 
     p.dt = (T)a->dt;
     p.rest = (T)a->restitution;
     p.fric = (T)a->friction;
+    for (int i = 0; i < 3; ++i) p.gdt[i] = p.g[i] * p.dt;
+    p.neg1pe = -((T)1 + p.rest);
     p.n_ground = a->n_ground_hits;
     p.n_pair = a->n_pair_hits;
     return p;
