@@ -294,7 +294,7 @@ def b200_arm(args):
     # per-env parameters (restitution, friction) cross HBM once per launch.
     flops_per_substep = 60.0 + 72.0 * i_per + 22.0 * (c_per - i_per)
     bytes_per_launch = E * (26 + 2) * esize
-    launch_ms = ms_per_step / (S // F)           # time per 128-substep advance of all E envs (two half-batch launches)
+    launch_ms = ms_per_step / (S // F)           # time per F-substep advance of all E envs (two half-batch launches)
     fused_tflops = E * F * flops_per_substep / (launch_ms * 1e-3) / 1e12
     fused_gbs = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     k1_gbs = bytes_per_launch / (k1_launch_ms * 1e-3) / 1e9
@@ -320,14 +320,17 @@ def b200_arm(args):
                          "flops_per_env_substep": flops_per_substep, "contacts_per_env_substep": c_per,
                          "impulses_per_env_substep": i_per, "launch_ms": launch_ms, "substeps_per_launch": F,
                          "hbm_GBps_of_same_launch": fused_gbs,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture
-                         # in profiles/r1_ncu_full_fast_kernel.csv (valid for the default 1,048,576-env fp64 shape only)
-                         "traffic": 194.2e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
+                         # dram__bytes_read.sum + dram__bytes_write.sum from the ncu --set full capture in
+                         # profiles/r1_ncu_full_pf_kernel.csv: 62.9 + 8.0 MB per half-batch launch, two launches per
+                         # advance of all envs (most of the 54.5 MB write-back is still in the 126 MB L2 when a launch
+                         # ends).  Valid for the default 1,048,576-env fp64 shape only.
+                         "traffic": 141.9e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
             "roofline_k1": {"bound": "hbm", "kernel": "same kernel, 1 substep per launch (the reference's per-frame call)",
                             "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
                             "peak_source": hbm_src, "frac_of_nominal_8TBps": k1_gbs / 8000.0,
                             "bytes_per_env": (26 + 2) * esize, "launch_ms": k1_launch_ms,
                             "env_steps_per_s": world * E / (k1_launch_ms * 1e-3),
+                            # ncu capture of the one-substep launches (profiles/r1_summary.md): 125.8 MB read + ~60 MB written
                             "traffic": 185.9e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
         }
         line["end_of_run_stats"] = stats
