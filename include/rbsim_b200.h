@@ -193,6 +193,13 @@ RBS_API int rbs_pack_state(int dtype, long n_env, int n_body, int body_fastest, 
 RBS_API int rbs_unpack_state(int dtype, long n_env, int n_body, int body_fastest, const void *state, long stride, void *qpos,
                      void *qvel, void *stream);
 
+/* mj_resetData for a subset of the batch (the viewer's BACKSPACE handler, src/viewer/mujoco_viewer.py:62-65):
+ * qpos <- qpos0[7 * n_body] (device, dtype), qvel <- 0 and the event counters <- 0 for every environment whose
+ * env_mask byte (device, [n_env]) is non-zero; env_mask == NULL resets all.  Counter arrays may be NULL; they are
+ * indexed like the state ([n_body][n_env] env-major, [n_env][n_body] body-fastest). */
+RBS_API int rbs_reset_envs(int dtype, long n_env, int n_body, int body_fastest, void *state, long stride, const void *qpos0,
+                   const unsigned char *env_mask, unsigned *n_contacts, unsigned *n_impulses, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer drivers: the call a reference-side `for _ in range(steps): step_function(model, data, dt)`
  * loop is replaced by.  qpos_host / qvel_host are HOST arrays in the reference layout

@@ -92,6 +92,7 @@ PROTOTYPES = {
     "rbs_step_multi_sphere": (c_int, [POINTER(MultiSphereArgs)]),
     "rbs_pack_state": (c_int, [c_int, c_long, c_int, c_int, c_void_p, c_void_p, c_void_p, c_long, c_void_p]),
     "rbs_unpack_state": (c_int, [c_int, c_long, c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p]),
+    "rbs_reset_envs": (c_int, [c_int, c_long, c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rbs_run_body_plane_host": (c_int, [POINTER(BodyPlaneArgs), c_void_p, c_void_p, c_long]),
     "rbs_run_two_ball_host": (c_int, [POINTER(TwoBallArgs), c_void_p, c_void_p, c_long]),
     "rbs_run_multi_sphere_host": (c_int, [POINTER(MultiSphereArgs), c_void_p, c_void_p, c_long]),

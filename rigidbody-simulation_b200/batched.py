@@ -168,7 +168,7 @@ class BatchedData:
         self.n_impulses = torch.zeros(E * B, dtype=torch.int32, device=self.device)
         self.qpos = StateView(self, 0, 7)
         self.qvel = StateView(self, 7, 6)
-        self.reset()
+        self._init_state()
 
     def rows(self, first, count):
         """state rows [first, first+count) as a [count, nfree, nenv] view (both layouts)."""
@@ -176,21 +176,38 @@ class BatchedData:
             return self.state[first:first + count]
         return self.state[first:first + count].view(count, self.nenv, self.nfree).permute(0, 2, 1)
 
-    def reset(self, env_mask=None):
-        """mj_resetData (src/viewer/mujoco_viewer.py:62-65): qpos0, zero velocities, time 0; optionally
-        only the environments selected by a boolean mask."""
+    def _init_state(self):
+        """Fresh buffers at construction: qpos0, zero velocities (plain fills -- allocation plumbing, also on a CPU device)."""
         q0 = torch.as_tensor(self.model.qpos0, dtype=self.dtype).to(self.device).view(self.nfree, 7).t()  # [7, nfree]
         rows = self.rows(0, ROWS)
+        rows[:7] = q0.unsqueeze(-1)
+        rows[7:] = 0
+        self.time = 0.0
+
+    def reset(self, env_mask=None):
+        """mj_resetData (src/viewer/mujoco_viewer.py:62-65): qpos0, zero velocities, zero event counters; optionally
+        only the environments selected by a boolean mask (host or device).  One launch of ``rbs_reset_envs`` on the
+        current stream, no host sync."""
+        import ctypes
+        from . import _lib, stepper
+        if self.device.type != "cuda":
+            raise _lib.RbsError("reset needs the CUDA extension and a CUDA device (there is no CPU fallback)")
+        if getattr(self, "_qpos0_dev", None) is None:
+            self._qpos0_dev = torch.as_tensor(self.model.qpos0, dtype=self.dtype).to(self.device).contiguous()
+        mask_ptr = None
+        if env_mask is not None:
+            m = torch.as_tensor(env_mask).to(device=self.device, dtype=torch.bool).contiguous()
+            if m.numel() != self.nenv:
+                raise ValueError(f"env_mask has {m.numel()} entries for {self.nenv} environments")
+            mask_u8 = m.view(torch.uint8)
+            mask_ptr = ctypes.c_void_p(mask_u8.data_ptr())
+        _lib.check(_lib.load().rbs_reset_envs(
+            stepper.rbs_dtype(self.dtype), self.nenv, self.nfree, 1 if self.layout == "body" else 0,
+            ctypes.c_void_p(self.state.data_ptr()), self.stride, ctypes.c_void_p(self._qpos0_dev.data_ptr()), mask_ptr,
+            ctypes.c_void_p(self.n_contacts.data_ptr()), ctypes.c_void_p(self.n_impulses.data_ptr()),
+            stepper.current_stream(self.device)))
         if env_mask is None:
-            rows[:7] = q0.unsqueeze(-1)
-            rows[7:] = 0
-            self.n_contacts.zero_()
-            self.n_impulses.zero_()
             self.time = 0.0
-        else:
-            m = torch.as_tensor(env_mask, dtype=torch.bool, device=self.device)
-            rows[:7] = torch.where(m, q0.unsqueeze(-1), rows[:7])
-            rows[7:] = torch.where(m, torch.zeros((), dtype=self.dtype, device=self.device), rows[7:])
 
     def set_state(self, qpos, qvel):
         """Load AoS host/device arrays qpos[nenv, 7*nfree], qvel[nenv, 6*nfree] (reference layout)."""

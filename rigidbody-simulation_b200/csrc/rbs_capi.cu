@@ -662,6 +662,23 @@ int rbs_unpack_state(int dtype, long n_env, int n_body, int body_fastest, const 
     return check_launch("rbs_unpack_state");
 }
 
+int rbs_reset_envs(int dtype, long n_env, int n_body, int body_fastest, void *state, long stride, const void *qpos0,
+                   const unsigned char *env_mask, unsigned *n_contacts, unsigned *n_impulses, void *stream) {
+    if (bad_dtype(dtype)) return fail(RBS_EINVAL, "rbs_reset_envs: bad dtype %d", dtype);
+    if (n_env < 0 || n_body < 1) return fail(RBS_EINVAL, "rbs_reset_envs: bad sizes");
+    if (n_env == 0) return RBS_OK;
+    if (!state || !qpos0) return fail(RBS_EINVAL, "rbs_reset_envs: null array");
+    if (stride < (body_fastest ? n_env * n_body : n_env)) return fail(RBS_EINVAL, "rbs_reset_envs: stride too small");
+    const unsigned grid = blocks_for(n_env * n_body, 256);
+    if (dtype == RBS_F64)
+        rbs::reset_envs_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(n_env, n_body, body_fastest, (double *)state, stride,
+                                                                             (const double *)qpos0, env_mask, n_contacts, n_impulses);
+    else
+        rbs::reset_envs_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(n_env, n_body, body_fastest, (float *)state, stride,
+                                                                            (const float *)qpos0, env_mask, n_contacts, n_impulses);
+    return check_launch("rbs_reset_envs");
+}
+
 // Pipelined over chunks of environments: while chunk c is being stepped, chunk c+1 is on its way in over PCIe
 // and chunk c-1 on its way out (three internal streams; the caller's stream is joined at the end).
 int rbs_run_body_plane_host(const rbs_body_plane_args *a, void *qpos_host, void *qvel_host, long total_steps) {

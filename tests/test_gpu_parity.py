@@ -657,6 +657,42 @@ def test_multi_sphere_ragged_and_maximum_body_counts(rb):
         assert (calls == cnt[0]).all() and (imps == cnt[1]).all(), B
 
 
+def test_reset_envs_kernel(rb):
+    """reset(env_mask) = mj_resetData on a subset (mujoco_viewer.py:62-65): masked environments go back to qpos0 with zero
+    velocity and zero event counters, the others are untouched bit for bit; both state layouts, fp64 and fp32,
+    host and device masks, and the unmasked form."""
+    from rigidbody_simulation_b200 import scenes, stepper
+    for layout, name, dtype in (("env", "sphere", torch.float64), ("env", "ball_collision", torch.float32),
+                                ("body", "multi_sphere", torch.float64)):
+        E = 1003
+        m = rb.BatchedModel.from_xml_path(scenes.model_path(name), nenv=E, device="cuda", dtype=dtype)
+        d = rb.BatchedData(m, layout=layout)
+        B = m.nfree
+        rng = np.random.default_rng(5)
+        qp, qv = rng.normal(size=(E, 7 * B)), rng.normal(size=(E, 6 * B))
+        d.set_state(qp, qv)
+        d.n_contacts.fill_(7)
+        d.n_impulses.fill_(3)
+        before_p, before_v = d.qpos.torch().clone(), d.qvel.torch().clone()
+        mask = rng.uniform(size=E) < 0.3
+        d.reset(mask if layout == "env" else torch.as_tensor(mask, device="cuda"))
+        q, v = d.qpos.torch(), d.qvel.torch()
+        sel = torch.as_tensor(mask, device="cuda")
+        q0 = torch.as_tensor(np.asarray(m.qpos0), dtype=dtype, device="cuda")
+        assert torch.equal(q[sel], q0.expand(int(sel.sum()), -1)) and (v[sel] == 0).all()
+        assert torch.equal(q[~sel], before_p[~sel]) and torch.equal(v[~sel], before_v[~sel])
+        if layout == "body":
+            nc = d.n_contacts.view(E, B)
+            assert (nc[sel] == 0).all() and (nc[~sel] == 7).all() and (d.n_impulses.view(E, B)[sel] == 0).all()
+        elif B == 1:
+            assert (d.n_contacts[sel] == 0).all() and (d.n_contacts[~sel] == 7).all()
+        d.reset()
+        assert torch.equal(d.qpos.torch(), q0.expand(E, -1)) and (d.qvel.torch() == 0).all()
+        assert (d.n_contacts == 0).all() and (d.n_impulses == 0).all()
+        with pytest.raises(ValueError):
+            d.reset(np.ones(E + 1, bool))
+
+
 def test_plane_frame_box_kernel_arbitrary_plane(rb):
     """The cube's fused fast launches also work in the plane frame: planes tilted about two axes and not through the
     origin, cubes dropped from just above the plane with random orientation and spin, threshold 1e-4.  Four fused
