@@ -41,7 +41,7 @@ def test_parser_matches_reference_model_values(golden):
 
 def test_parser_templating_and_errors():
     from rigidbody_simulation_b200 import mjcf
-    txt = ('<mujoco><option gravity="0 0 -9.8" timestep="{TIMESTEP}"/><worldbody>'
+    txt = ('<mujoco><compiler angle="radian"/><option gravity="0 0 -9.8" timestep="{TIMESTEP}"/><worldbody>'
            '<geom type="plane" size="1 1 1" euler="{INCLINE_ANGLE} 0 0"/>'
            '<body name="b" pos="0 0 1"><freejoint/><geom type="box" size="0.3 0.2 0.1" density="50"/></body>'
            '</worldbody></mujoco>')
@@ -55,7 +55,7 @@ def test_parser_templating_and_errors():
     with pytest.raises(ValueError):
         mjcf.parse_string('<mujoco><worldbody><geom type="capsule" size="1 1"/></worldbody></mujoco>')
     with pytest.raises(ValueError):
-        mjcf.parse_string('<mujoco><compiler angle="degree"/><worldbody/></mujoco>')
+        mjcf.parse_string('<mujoco><compiler angle="gradian"/><worldbody/></mujoco>')
     with pytest.raises(ValueError):
         mjcf.parse_string("<notmujoco/>")
 
@@ -193,6 +193,70 @@ def test_batched_data_views_on_cpu():
         mask = torch.tensor([True, False, False, True, False])
         with pytest.raises(rb.RbsError):          # reset(env_mask) is a CUDA kernel (rbs_reset_envs): no CPU path
             d.reset(mask)
+
+
+def test_parser_orientation_specifiers_units_and_defaults():
+    """N1 front-end: every MuJoCo orientation specifier, degree / radian, eulerseq (lower = rotating frame, upper =
+    fixed frame), top-level geom defaults, explicit geom mass, <inertial> under inertiafromgeom auto / false --
+    checked against SciPy's Rotation and the closed-form mass rules."""
+    from scipy.spatial.transform import Rotation
+    from rigidbody_simulation_b200 import mjcf
+
+    def body_quat(compiler, attr):
+        sc = mjcf.parse_string(f'<mujoco>{compiler}<worldbody><body {attr}><freejoint/><geom type="sphere" size="0.1"/></body>'
+                               '</worldbody></mujoco>')
+        return np.array(sc.bodies[1].quat)
+
+    def same_rotation(q_wxyz, rot):
+        want = rot.as_quat()[[3, 0, 1, 2]]
+        return min(np.abs(q_wxyz - want).max(), np.abs(q_wxyz + want).max()) < 1e-14
+
+    rad = '<compiler angle="radian"/>'
+    e = [0.3, -1.1, 2.0]
+    assert same_rotation(body_quat(rad, f'euler="{e[0]} {e[1]} {e[2]}"'), Rotation.from_euler("XYZ", e))       # SciPy: upper = intrinsic
+    assert same_rotation(body_quat('<compiler angle="radian" eulerseq="XYZ"/>', f'euler="{e[0]} {e[1]} {e[2]}"'),
+                         Rotation.from_euler("xyz", e))                                                         # fixed frame
+    assert same_rotation(body_quat('<compiler angle="radian" eulerseq="zyx"/>', f'euler="{e[0]} {e[1]} {e[2]}"'),
+                         Rotation.from_euler("ZYX", e))
+    d = np.degrees(e)
+    assert same_rotation(body_quat("", f'euler="{d[0]} {d[1]} {d[2]}"'), Rotation.from_euler("XYZ", e))          # default unit: degree
+    assert same_rotation(body_quat("", 'axisangle="0 3 4 90"'), Rotation.from_rotvec(np.array([0, 0.6, 0.8]) * np.pi / 2))
+    assert same_rotation(body_quat(rad, 'axisangle="1 0 0 0.7"'), Rotation.from_euler("x", 0.7))
+    assert same_rotation(body_quat(rad, 'quat="2 0 0 2"'), Rotation.from_euler("z", np.pi / 2))
+    R = Rotation.from_euler("XYZ", e).as_matrix()
+    x, y = R[:, 0], R[:, 1]
+    assert same_rotation(body_quat(rad, 'xyaxes="%s"' % " ".join(repr(float(c)) for c in (*(2 * x), *(y + 0.3 * x)))), Rotation.from_matrix(R))
+    z = np.array([0.2, -0.5, 0.7]); z /= np.linalg.norm(z)
+    qz = body_quat(rad, 'zaxis="%s"' % " ".join(repr(float(c)) for c in 3 * z))
+    assert np.abs(Rotation.from_quat(qz[[1, 2, 3, 0]]).apply([0, 0, 1]) - z).max() < 1e-15
+    assert abs(qz[3]) < 1e-15                                              # minimal rotation: no twist about z
+    assert body_quat(rad, 'zaxis="0 0 -2"').tolist() == [0.0, 1.0, 0.0, 0.0]
+    with pytest.raises(ValueError):
+        body_quat(rad, 'euler="0 0 1" quat="1 0 0 0"')
+    with pytest.raises(ValueError):
+        body_quat(rad, 'quat="0 0 0 0"')
+
+    sc = mjcf.parse_string('<mujoco><compiler angle="radian" inertiafromgeom="true"/><default><geom density="50" type="box" size="0.1 0.2 0.3"/>'
+                           '</default><worldbody><geom type="plane" size="1 1 1" zaxis="0 -1 1"/>'
+                           '<body><freejoint/><geom/><inertial pos="0 0 0" mass="9" diaginertia="1 1 1"/></body>'
+                           '<body><freejoint/><geom type="sphere" size="0.2" mass="3"/></body></worldbody></mujoco>')
+    m = 50 * 8 * 0.1 * 0.2 * 0.3
+    assert sc.bodies[1].mass == pytest.approx(m, rel=1e-15)                # inertiafromgeom="true" overrides <inertial>
+    assert sc.bodies[1].inertia == pytest.approx([m / 3 * 0.13, m / 3 * 0.10, m / 3 * 0.05], rel=1e-14)
+    assert sc.bodies[2].mass == 3.0 and sc.bodies[2].inertia == pytest.approx([0.4 * 3 * 0.04] * 3, rel=1e-15)
+    _, n = mjcf.plane_frame(sc, sc.planes()[0])
+    assert n == pytest.approx([0, -math.sqrt(0.5), math.sqrt(0.5)], abs=1e-15)
+    auto = mjcf.parse_string('<mujoco><worldbody><body><freejoint/><geom type="sphere" size="0.2"/>'
+                             '<inertial pos="0 0 0" mass="9" diaginertia="1 2 3"/></body></worldbody></mujoco>')
+    assert auto.bodies[1].mass == 9.0 and auto.bodies[1].inertia == [1.0, 2.0, 3.0]
+    for bad in ('<mujoco><compiler inertiafromgeom="false"/><worldbody><body><freejoint/><geom type="sphere" size="0.2"/></body></worldbody></mujoco>',
+                '<mujoco><worldbody><body><freejoint/><geom type="sphere" size="0.2"/><inertial pos="0 0 0.1" mass="1" diaginertia="1 1 1"/></body></worldbody></mujoco>',
+                '<mujoco><worldbody><body><joint type="hinge"/><geom type="sphere" size="0.2"/></body></worldbody></mujoco>',
+                '<mujoco><worldbody><body><freejoint/><geom type="box" size="0.2"/></body></worldbody></mujoco>',
+                '<mujoco><default><default class="a"/></default><worldbody/></mujoco>',
+                '<mujoco><worldbody><body><freejoint/><geom type="sphere" size="0.2" pos="0 0 0.1"/></body></worldbody></mujoco>'):
+        with pytest.raises(ValueError):
+            mjcf.parse_string(bad)
 
 
 def test_cli_help_and_headless_flags():
