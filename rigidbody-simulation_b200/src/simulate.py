@@ -26,6 +26,9 @@ def run_simulation(sim_name, steps=None, envs=1, dtype="fp64", substeps=1, devic
     import numpy as np
     import torch
 
+    if not torch.cuda.is_available():
+        print("No CUDA device: the stepping path runs as sm_100a kernels only (there is no CPU fallback)")
+        sys.exit(1)
     from .simulation import ball_collision, cube_incline, multi_sphere_bounce, single_sphere_bounce
     tdtype = {"fp64": torch.float64, "fp32": torch.float32}[dtype]
     t0 = time.time()
