@@ -128,6 +128,11 @@ typedef struct rbs_body_plane_args {
     double contact_threshold;  /* contacts with |dist| < threshold are skipped (collision.py:79-80) */
     unsigned *n_contacts;      /* [n_env] += contacts handed to the impulse routine, or NULL */
     unsigned *n_impulses;      /* [n_env] += contacts that produced an impulse (u_n < 0), or NULL */
+    void *trajectory;          /* [substeps][trajectory_envs][3] (dtype, device) or NULL: position of the first
+                                  trajectory_envs environments after EVERY substep of the launch -- what the reference's
+                                  logger.record sees per frame (src/viewer/mujoco_viewer.py:116-119).  Device-resident
+                                  stepping only (rbs_run_body_plane_host refuses it). */
+    long trajectory_envs;      /* clamped to n_env; ignored when trajectory is NULL */
     void *stream;
 } rbs_body_plane_args;
 RBS_API int rbs_step_body_plane(const rbs_body_plane_args *a);

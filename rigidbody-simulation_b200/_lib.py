@@ -37,6 +37,7 @@ class BodyPlaneArgs(Structure):
         ("plane_point", D3), ("plane_normal", D3), ("gravity", D3),
         ("dt", c_double), ("contact_threshold", c_double),
         ("n_contacts", c_void_p), ("n_impulses", c_void_p),
+        ("trajectory", c_void_p), ("trajectory_envs", c_long),
         ("stream", c_void_p),
     ]
 

@@ -122,6 +122,8 @@ template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_a
     }
     p.n_contacts = a->n_contacts ? a->n_contacts + w.off : nullptr;
     p.n_impulses = a->n_impulses ? a->n_impulses + w.off : nullptr;
+    p.traj = static_cast<T *>(a->trajectory);
+    p.traj_envs = a->trajectory ? (a->trajectory_envs < w.cnt ? a->trajectory_envs : w.cnt) : 0;
     return p;
 }
 
@@ -163,7 +165,7 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
         return;
     }
     static const int pf_min = [] { const char *e = getenv("RBS_PF_MIN_SUBSTEPS"); return e ? atoi(e) : 4; }();
-    if (a->substeps >= pf_min) {        // fused launches: work in the plane frame (two rotations per launch pay off)
+    if (a->substeps >= pf_min && !a->trajectory) {   // fused launches: work in the plane frame (two rotations per launch pay off)
         const bool count = a->n_contacts || a->n_impulses, thr = a->contact_threshold > 0;
         const bool wide = tuning_minb(a->substeps, RBS_ARITH_FAST) == 8;
 #define RBS_PF(MINB, COUNT, THR) rbs::step_sphere_plane_pf_kernel<T, MINB, COUNT, THR><<<grid, rbs::kBlock, 0, st>>>(p)
@@ -185,7 +187,7 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
 template <typename T> void launch_box_plane_fast(const rbs_body_plane_args *a, const Window &w) {
     const rbs::BodyPlaneParams<T> p = make_params<T>(a, w);
     static const int pf_min = [] { const char *e = getenv("RBS_PF_MIN_SUBSTEPS"); return e ? atoi(e) : 4; }();
-    if (!a->xfrc && a->substeps >= pf_min) {   // fused launches: plane frame (two rotations per launch pay off)
+    if (!a->xfrc && !a->trajectory && a->substeps >= pf_min) {   // fused launches: plane frame (two rotations per launch pay off)
         // resident CTAs per SM (register cap 128 / 96 / 80); measured on B200, 1M cubes fp64, 128 fused substeps:
         // 6.14e10 / 6.49e10 / 6.55e10 env-substeps/s bouncing, 4.39e10 / 4.63e10 / 4.69e10 sliding on the incline
         static const int minb = [] { const char *e = getenv("RBS_BOX_MINB"); return e ? atoi(e) : 6; }();
@@ -232,6 +234,7 @@ int validate_body_plane(const rbs_body_plane_args *a, bool need_state) {
     if (a->substeps < 1) return fail(RBS_EINVAL, "rbs_step_body_plane: substeps %d < 1", a->substeps);
     if (a->param_stride != 0 && a->param_stride < a->n_env)
         return fail(RBS_EINVAL, "rbs_step_body_plane: param_stride %ld < n_env %ld", a->param_stride, a->n_env);
+    if (a->trajectory && a->trajectory_envs < 0) return fail(RBS_EINVAL, "rbs_step_body_plane: trajectory_envs %ld < 0", a->trajectory_envs);
     if (need_state) {
         if (a->n_env > 0 && !a->state) return fail(RBS_EINVAL, "rbs_step_body_plane: null state");
         if (a->stride < a->n_env) return fail(RBS_EINVAL, "rbs_step_body_plane: stride %ld < n_env %ld", a->stride, a->n_env);
@@ -685,6 +688,7 @@ int rbs_run_body_plane_host(const rbs_body_plane_args *a, void *qpos_host, void 
     int rc = validate_body_plane(a, false);
     if (rc) return rc;
     if (total_steps < 0) return fail(RBS_EINVAL, "total_steps %ld < 0", total_steps);
+    if (a->trajectory) return fail(RBS_EINVAL, "rbs_run_body_plane_host: trajectory sampling needs device-resident stepping");
     if (a->n_env == 0) return RBS_OK;
     if (!qpos_host || !qvel_host) return fail(RBS_EINVAL, "null host buffer");
     std::lock_guard<std::mutex> lock(g_ws_mutex);

@@ -38,16 +38,47 @@ class TrajectoryLog:
         self.t[i] = time_point
         self.n += 1
 
+    def window(self, count, time0, dt):
+        """The next ``count`` rows as a contiguous ``[count, n_sample, 3]`` device view for a fused launch to fill
+        (``trajectory=`` of the step functions); stamps their times ``time0 + (i+1)*dt`` as the per-frame loop would."""
+        i = self.n
+        if i + count > self.buf.shape[0]:
+            raise IndexError("TrajectoryLog is full")
+        self.t[i:i + count] = time0 + dt * np.arange(1, count + 1)
+        self.n += count
+        return self.buf[i:i + count]
+
     def finish(self):
         host = self.buf[: self.n].cpu().numpy()
         self.times = self.t[: self.n].tolist()
         self.x_positions, self.y_positions, self.z_positions = (host[:, 0, c].tolist() for c in range(3))
         return host
 
+    def save_npz(self, path):
+        """times [n] and positions [n, n_sample, 3] (x, y, z) of everything recorded so far."""
+        np.savez(path, times=self.t[: self.n], positions=self.buf[: self.n].cpu().numpy())
 
-def start_main_loop(model, data, step_function, steps, logger=None):
-    """Runs ``steps`` iterations of the reference's loop body; returns the accumulated simulation time."""
+
+def start_main_loop(model, data, step_function, steps, logger=None, substeps_per_launch=1):
+    """Runs ``steps`` iterations of the reference's loop body; returns the accumulated simulation time.
+
+    ``substeps_per_launch = K > 1`` fuses K iterations into each call of ``step_function`` (which must accept the
+    ``substeps`` keyword); with a :class:`TrajectoryLog` the kernel itself records the sampled environments' position
+    after every one of the K steps (``trajectory=``), so the log is the one the per-frame loop would have written."""
     simulation_time = 0.0
+    K = int(substeps_per_launch)
+    if K > 1:
+        done = 0
+        while done < int(steps):
+            k = min(K, int(steps) - done)
+            if isinstance(logger, TrajectoryLog):
+                step_function(model, data, dt=model.opt.timestep, substeps=k,
+                              trajectory=logger.window(k, simulation_time, model.opt.timestep))
+            else:
+                step_function(model, data, dt=model.opt.timestep, substeps=k)
+            simulation_time += model.opt.timestep * k
+            done += k
+        return simulation_time
     for _ in range(int(steps)):
         pos_new = step_function(model, data, dt=model.opt.timestep)
         simulation_time += model.opt.timestep

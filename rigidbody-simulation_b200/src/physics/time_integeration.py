@@ -14,17 +14,18 @@ from .physics_utils import apply_impulse_friction  # noqa: F401  (:5)
 
 
 def timestep_integration(model, obj, data, dt=0.01, restitution=1.0, friction_coeff=0.5, contact_threshold=1e-4,
-                         substeps=1, arith="strict"):
+                         substeps=1, arith="strict", trajectory=None):
     mj.mj_forward(model, data)                                              # :29
     body_id = mj.mj_name2id(model, mj.mjtObj.mjOBJ_BODY, f"{obj}")          # :30
     stepper.step_body_plane(model, data, body_id, dt, restitution, friction_coeff, contact_threshold,
-                            scheme=RBS_SCHEME_A, substeps=substeps, arith=arith)
+                            scheme=RBS_SCHEME_A, substeps=substeps, arith=arith, trajectory=trajectory)
     return _position(data)
 
 
-def general(model, obj, data, dt=0.01, restitution=1.0, friction_coeff=0.5, contact_threshold=1e-4, substeps=1):
+def general(model, obj, data, dt=0.01, restitution=1.0, friction_coeff=0.5, contact_threshold=1e-4, substeps=1,
+            trajectory=None):
     mj.mj_forward(model, data)                                              # :95
     body_id = mj.mj_name2id(model, mj.mjtObj.mjOBJ_BODY, f"{obj}")          # :96
     stepper.step_body_plane(model, data, body_id, dt, restitution, friction_coeff, contact_threshold,
-                            scheme=RBS_SCHEME_GENERAL, substeps=substeps)
+                            scheme=RBS_SCHEME_GENERAL, substeps=substeps, trajectory=trajectory)
     return _position(data)

@@ -13,7 +13,7 @@ import time
 SIMULATIONS = ["cube_incline", "ball_collision", "single_sphere", "compare_builtin", "multi_sphere"]
 
 
-def run_simulation(sim_name, steps=None, envs=1, dtype="fp64", substeps=1, device=None):
+def run_simulation(sim_name, steps=None, envs=1, dtype="fp64", substeps=1, device=None, log_path=None):
     if sim_name not in SIMULATIONS:
         print(f"Unknown simulation name: '{sim_name}'")
         print("Available simulations:")
@@ -33,14 +33,21 @@ def run_simulation(sim_name, steps=None, envs=1, dtype="fp64", substeps=1, devic
     tdtype = {"fp64": torch.float64, "fp32": torch.float32}[dtype]
     t0 = time.time()
     if sim_name == "single_sphere":
-        model, data, _ = single_sphere_bounce.run_headless(steps or 2000, envs, device, tdtype, log=False)
+        model, data, logger = single_sphere_bounce.run_headless(steps or 2000, envs, device, tdtype, log=log_path is not None,
+                                                                substeps_per_launch=substeps)
     elif sim_name == "cube_incline":
-        model, data, _ = cube_incline.run_headless(steps or 240, envs, device, tdtype, log=False)
+        model, data, logger = cube_incline.run_headless(steps or 240, envs, device, tdtype, log=log_path is not None,
+                                                        substeps_per_launch=substeps)
     elif sim_name == "ball_collision":
-        model, data, _ = ball_collision.run_headless(steps or 500, envs, device, tdtype, substeps)
+        model, data, logger = ball_collision.run_headless(steps or 500, envs, device, tdtype, substeps)
     else:
-        model, data, _ = multi_sphere_bounce.run_headless(steps or 300, envs, device, tdtype, substeps)
+        model, data, logger = multi_sphere_bounce.run_headless(steps or 300, envs, device, tdtype, substeps)
     torch.cuda.synchronize()
+    if log_path is not None:
+        if not hasattr(logger, "save_npz"):
+            print(f"--log is available for single_sphere and cube_incline (the single-body steppers), not {sim_name}")
+            sys.exit(1)
+        logger.save_npz(log_path)
     contacts, impulses = data.counters()
     out = {"sim": sim_name, "envs": envs, "dtype": dtype, "wall_s": round(time.time() - t0, 4),
            "qpos_env0": np.asarray(data.qpos).reshape(envs, -1)[0].tolist(),
@@ -59,8 +66,11 @@ def main(argv=None):
     parser.add_argument("--substeps-per-launch", type=int, default=1)
     parser.add_argument("--seed", type=int, default=20261018)
     parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--log", type=str, default=None, metavar="PATH.npz",
+                        help="save times [n] and positions [n, sampled envs, 3] of every step (recorded on the device, also "
+                             "inside fused launches) -- the data behind the reference's height-vs-time plots")
     args = parser.parse_args(argv)
-    run_simulation(args.sim, args.steps, args.envs, args.dtype, args.substeps_per_launch)
+    run_simulation(args.sim, args.steps, args.envs, args.dtype, args.substeps_per_launch, log_path=args.log)
 
 
 if __name__ == "__main__":

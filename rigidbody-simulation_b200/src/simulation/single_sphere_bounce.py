@@ -34,15 +34,16 @@ def build(nenv=1, device=None, dtype=torch.float64):
     return model, data
 
 
-def sphere_simulation_step(model, data, dt, substeps=1):
+def sphere_simulation_step(model, data, dt, substeps=1, trajectory=None):
     return custom_step_with_impulse_collision_friction(model, "sphere", data, dt=dt, restitution=restitution,
-                                                       friction_coeff=friction_coefficient, substeps=substeps)
+                                                       friction_coeff=friction_coefficient, substeps=substeps,
+                                                       trajectory=trajectory)
 
 
-def run_headless(steps=2000, nenv=1, device=None, dtype=torch.float64, log=True):
+def run_headless(steps=2000, nenv=1, device=None, dtype=torch.float64, log=True, substeps_per_launch=1):
     model, data = build(nenv, device, dtype)
     logger = TrajectoryLog(steps, min(nenv, 4), model.device, dtype) if log else None
-    start_main_loop(model, data, sphere_simulation_step, steps, logger)
+    start_main_loop(model, data, sphere_simulation_step, steps, logger, substeps_per_launch)
     if logger is not None:
         logger.finish()
     return model, data, logger

@@ -133,7 +133,8 @@ def _key_of(value):
 
 
 def step_body_plane(model, data, body_id, dt, restitution, friction_coeff, contact_threshold,
-                    scheme=RBS_SCHEME_A, substeps=1, count=True, strict_inertia=None, arith="strict", env_range=None):
+                    scheme=RBS_SCHEME_A, substeps=1, count=True, strict_inertia=None, arith="strict", env_range=None,
+                    trajectory=None):
     """arith: "strict" reproduces the reference's rounding sequence; "fast" re-associates for the FP pipe
     (scheme A + isotropic inertia only; <= 1e-12 relative per step in fp64).
 
@@ -158,6 +159,18 @@ def step_body_plane(model, data, body_id, dt, restitution, friction_coeff, conta
         a = body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold, scheme, substeps,
                             count, strict_inertia, arith, env_range)
     a.stream = current_stream(model.device)
+    # trajectory: device tensor [substeps, n, 3] that receives the position of the first n environments after every
+    # substep of this launch (the per-frame logger.record of the reference, without leaving the fused launch)
+    if trajectory is not None:
+        if (not torch.is_tensor(trajectory) or trajectory.device != data.state.device or trajectory.dtype != model.dtype
+                or trajectory.dim() != 3 or trajectory.shape[0] != int(substeps) or trajectory.shape[2] != 3
+                or not trajectory.is_contiguous()):
+            raise ValueError("trajectory must be a contiguous device tensor [substeps, n_sample, 3] of the model's dtype")
+        if trajectory.shape[1] > a.n_env:
+            raise ValueError(f"trajectory samples {trajectory.shape[1]} environments, the launch steps {a.n_env}")
+        a.trajectory, a.trajectory_envs = _ptr(trajectory), int(trajectory.shape[1])
+    else:
+        a.trajectory, a.trajectory_envs = None, 0
     _lib.check(_lib.load().rbs_step_body_plane(ctypes.byref(a)))
 
 

@@ -657,6 +657,56 @@ def test_multi_sphere_ragged_and_maximum_body_counts(rb):
         assert (calls == cnt[0]).all() and (imps == cnt[1]).all(), B
 
 
+def test_in_kernel_trajectory_equals_per_frame_logging(rb, tmp_path, golden):
+    """A fused launch with ``trajectory=`` writes, for the sampled environments, exactly the positions the per-frame
+    loop (one launch and one logger.record per step, mujoco_viewer.py:113-119) logs: config 1 (2000 steps, the
+    height-vs-time curve of data/plots/single_sphere/height_vs_time.png) and the cube on the incline, strict policy
+    bit for bit; fast policy and a batch with a window, within the per-step bar.  Also the CLI's --log."""
+    import json
+    from rigidbody_simulation_b200 import headless, stepper, synth
+    from rigidbody_simulation_b200.src import simulate
+    from rigidbody_simulation_b200.src.simulation import cube_incline, single_sphere_bounce
+    for mod, steps in ((single_sphere_bounce, 2000), (cube_incline, 240)):
+        _, _, per_frame = mod.run_headless(steps, nenv=3)
+        _, d_fused, fused = mod.run_headless(steps, nenv=3, substeps_per_launch=173)
+        a, b = per_frame.finish(), fused.finish()
+        assert a.shape == b.shape == (steps, 3, 3) and np.array_equal(a, b)
+        assert np.allclose(per_frame.times, fused.times, rtol=0, atol=1e-12)
+        assert fused.z_positions == per_frame.z_positions
+    # known answer of SURVEY section 4: first rebound peak of the shipped sphere scene, 1.4776 at t = 1.116 s
+    _, _, lg = single_sphere_bounce.run_headless(2000, nenv=1, substeps_per_launch=500)
+    lg.finish()
+    z, t = np.array(lg.z_positions), np.array(lg.times)
+    k = 60 + int(np.argmax(z[60:200]))
+    assert z[k] == pytest.approx(1.4776, abs=2e-4) and t[k] == pytest.approx(1.116, abs=0.01)
+    # a batch, fast policy, sampled window of 5 envs out of 4096: equals stepping one substep at a time
+    E, K = 4096, 37
+    s = synth.sphere_incline(E)
+    for arith, tol in (("strict", 0.0), ("fast", 1e-12)):
+        model, data = make_single(rb, "sphere", [0.2], 0.7, s["qpos"], s["qvel"])
+        model.set_per_env(restitution=s["restitution"], friction=s["friction"])
+        traj = torch.full((K, 5, 3), float("nan"), dtype=torch.float64, device="cuda")
+        stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=K, arith=arith, trajectory=traj)
+        model2, data2 = make_single(rb, "sphere", [0.2], 0.7, s["qpos"], s["qvel"])
+        model2.set_per_env(restitution=s["restitution"], friction=s["friction"])
+        want = []
+        for _ in range(K):
+            stepper.step_body_plane(model2, data2, -1, s["dt"], None, None, 0.0, substeps=1, arith=arith)
+            want.append(data2.qpos.torch()[:5, :3].clone())
+        want = torch.stack(want)
+        if tol == 0.0:
+            assert torch.equal(traj, want)
+        else:
+            assert float(((traj - want).abs() / want.abs().clamp_min(1e-3)).max()) <= tol * K
+        assert comp_rel_err(data.qpos.torch().cpu().numpy(), data2.qpos.torch().cpu().numpy(), 1e-3) <= tol * K
+    with pytest.raises(ValueError):
+        stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=K + 1, trajectory=traj)
+    out = tmp_path / "traj.npz"
+    simulate.main(["--sim", "single_sphere", "--headless", "--steps", "300", "--substeps-per-launch", "64", "--log", str(out)])
+    z = np.load(out)
+    assert z["positions"].shape == (300, 1, 3) and z["times"].shape == (300,) and np.isfinite(z["positions"]).all()
+
+
 def test_reset_envs_kernel(rb):
     """reset(env_mask) = mj_resetData on a subset (mujoco_viewer.py:62-65): masked environments go back to qpos0 with zero
     velocity and zero event counters, the others are untouched bit for bit; both state layouts, fp64 and fp32,
