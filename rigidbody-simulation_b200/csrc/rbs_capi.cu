@@ -142,6 +142,11 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
     const rbs::BodyPlaneParams<T> p = make_params<T>(a, w);
     const unsigned grid = blocks_for(w.cnt, rbs::kBlock);
     cudaStream_t st = w.stream;
+    if (a->trajectory) {                     // per-substep position log of the sampled environments
+        if (a->inertia_mode == RBS_INERTIA_ISOTROPIC) rbs::step_body_plane_kernel<T, GEOM, SCHEME, 1, 4, true><<<grid, rbs::kBlock, 0, st>>>(p);
+        else rbs::step_body_plane_kernel<T, GEOM, SCHEME, 0, 2, true><<<grid, rbs::kBlock, 0, st>>>(p);
+        return;
+    }
     if (a->inertia_mode == RBS_INERTIA_ISOTROPIC) {
         if (GEOM == 0 && SCHEME == 0) {      // occupancy variants of the headline kernel
             switch (tuning_minb(a->substeps, RBS_ARITH_STRICT)) {
