@@ -329,6 +329,11 @@ def b200_arm(args):
                             "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
                             "peak_source": hbm_src, "frac_of_nominal_8TBps": k1_gbs / 8000.0,
                             "bytes_per_env": (26 + 2) * esize, "launch_ms": k1_launch_ms,
+                            "note": ("back-to-back launches; the state (%.0f MB) is larger than what the 126 MB L2 can keep "
+                                     "between a launch's write and the next launch's read (ncu: reads come from DRAM)"
+                                     % (E * 13 * esize / 1e6)) if E * 26 * esize > 126e6 else
+                                    ("state %.0f MB read + written per launch fits the 126 MB L2: this figure is L2-assisted, "
+                                     "not an HBM measurement" % (E * 13 * esize / 1e6)),
                             "env_steps_per_s": world * E / (k1_launch_ms * 1e-3),
                             # ncu capture of the one-substep launches (profiles/r1_summary.md): 125.8 MB read + ~60 MB written
                             "traffic": 185.9e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
