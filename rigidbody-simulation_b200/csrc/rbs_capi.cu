@@ -307,6 +307,8 @@ template <typename T> rbs::MultiSphereParams<T> make_params(const rbs_multi_sphe
     p.dt = (T)a->dt;
     p.rest = (T)a->restitution;
     p.fric = (T)a->friction;
+    for (int i = 0; i < 3; ++i) p.gdt[i] = p.g[i] * p.dt;
+    p.hdt = (T)0.5 * p.dt;
     // 0 = adaptive per CTA, starting at 50 % (or at RBS_MS_SKIN_PERCENT); > 0 = pinned; < 0 = no lists.  A launch of
     // fewer than 4 substeps (the reference's per-frame call) cannot amortise a list and scans every substep.
     static const int default_skin = [] { const char *e = getenv("RBS_MS_SKIN_PERCENT"); const int v = e ? atoi(e) : 50; return v > 0 ? v : 50; }();
