@@ -49,6 +49,21 @@ def test_struct_layout_matches_header():
     assert sizes == [ctypes.sizeof(_lib.BodyPlaneArgs), ctypes.sizeof(_lib.TwoBallArgs), ctypes.sizeof(_lib.MultiSphereArgs)]
 
 
+def test_integration_doc_stub_matches_the_abi():
+    """The ctypes stub INTEGRATION.md tells a maintainer to paste has the field order and size of the real struct."""
+    from rigidbody_simulation_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    start = text.index("class BodyPlaneArgs(ctypes.Structure)")
+    block = text[start:text.index("\n\n", start)]
+    ns = {"ctypes": ctypes}
+    exec(block, ns)
+    doc = ns["BodyPlaneArgs"]
+    assert [f[0] for f in doc._fields_] == [f[0] for f in _lib.BodyPlaneArgs._fields_]
+    assert ctypes.sizeof(doc) == ctypes.sizeof(_lib.BodyPlaneArgs)
+    for name, *_ in doc._fields_:
+        assert getattr(doc, name).offset == getattr(_lib.BodyPlaneArgs, name).offset, name
+
+
 def test_argument_validation_needs_no_gpu():
     from rigidbody_simulation_b200 import _lib
     lib = _lib.load()
@@ -96,3 +111,32 @@ def test_plain_c_client_runs_config1(tmp_path, golden):
     assert vals[0] == 0.0 and vals[1] == 0.0 and vals[3:7] == [1.0, 0.0, 0.0, 0.0]
     assert vals[2] == pytest.approx(0.20844281676054977, rel=1e-12)       # SURVEY Appendix B, from-rest variant
     assert vals[7] == pytest.approx(0.1051418877747299, rel=1e-11)
+
+
+@pytest.mark.gpu
+def test_integration_doc_stub_runs(monkeypatch):
+    """Section 2 of INTEGRATION.md, pasted as is: its step_many advances host qpos / qvel like the oracle does."""
+    import sys
+    import types
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle as co
+    from rigidbody_simulation_b200 import synth
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    start = text.index("```python", text.index("## 2. Call the C ABI directly")) + len("```python")
+    block = text[start:text.index("```", start)]
+    monkeypatch.chdir(ROOT)
+    ns = {}
+    exec(block, ns)
+    E = 3000
+    s = synth.sphere_incline(E)
+    m, inertia = 50 * 4 / 3 * np.pi * 0.2 ** 3, 0.4 * (50 * 4 / 3 * np.pi * 0.2 ** 3) * 0.04
+    model = types.SimpleNamespace(body_mass=[0.0, m], body_inertia=[[0.0] * 3, [inertia] * 3],
+                                  opt=types.SimpleNamespace(gravity=[0.0, 0.0, -9.8], timestep=0.009))
+    qp, qv = s["qpos"].copy(), s["qvel"].copy()
+    ns["step_many"](model, qp, qv, 100, 0.8, 0.4)
+    rq, rv = s["qpos"].copy(), s["qvel"].copy()
+    co.step_body_plane(rq, rv, 100, geom="sphere", mass=m, inertia=[inertia] * 3, size=0.2, plane_pos=[0, 0, 0],
+                       plane_normal=[0, 0, 1], gravity=[0, 0, -9.8], dt=0.009, restitution=0.8, friction=0.4, threshold=0.0)
+    assert np.max(np.abs(qp - rq) / np.maximum(np.abs(rq), 1e-3)) <= 1e-10
+    assert np.max(np.abs(qv - rv) / np.maximum(np.abs(rv), 1e-3)) <= 1e-10
