@@ -1079,3 +1079,35 @@ def test_plane_frame_kernel_arbitrary_plane(rb, dtype, tol):
             calls, imps = data.counters()
             assert (calls[:, 0] == cnt[0]).all() and (imps[:, 0] == cnt[1]).all(), euler
             assert cnt[0].sum() > E
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fused_launch_survives_fast_spin(rb, dtype):
+    """The fused fast kernels carry the orientation unnormalised between rescales (kRenormMask in rbs_kernels.cuh).
+    Spheres in free flight spinning at up to 2e4 rad/s (|0.5*dt*w| ~ 90 per substep; a 32-substep rescale interval
+    overflows float at ~4): 256 fused substeps must return finite unit quaternions that agree with 256 single-substep
+    launches of the same policy, which normalise after every substep like the reference (collision.py:94-95)."""
+    from rigidbody_simulation_b200 import stepper
+    rng = np.random.default_rng(5)
+    E = 4096
+    q = rng.normal(size=(E, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    qpos = np.concatenate([rng.uniform(-1, 1, (E, 2)), rng.uniform(500, 600, (E, 1)), q], axis=1)    # never reaches the plane
+    spin = rng.normal(size=(E, 3))
+    spin *= (np.geomspace(1.0, 2e4, E) / np.linalg.norm(spin, axis=1))[:, None]
+    qvel = np.concatenate([rng.uniform(-1, 1, (E, 3)), spin], axis=1)
+    out = {}
+    for K in (256, 1):
+        model, data = make_single(rb, "sphere", [0.2], 0.7, qpos, qvel, dtype=dtype)
+        for _ in range(256 // K):
+            stepper.step_body_plane(model, data, -1, 0.009, 0.9, 0.5, 0.0, substeps=K, arith="fast")
+        out[K] = state_of(data)
+    gq, gv = out[256]
+    assert np.isfinite(gq).all() and np.isfinite(gv).all()
+    tol = 1e-9 if dtype == np.float64 else 2e-3           # 256 steps of rounding at up to 90 rad per substep
+    assert np.max(np.abs(np.linalg.norm(gq[:, 3:], axis=1) - 1)) < (1e-12 if dtype == np.float64 else 1e-5)
+    # q and -q are the same orientation; compare up to sign
+    dq = np.minimum(np.abs(gq[:, 3:] - out[1][0][:, 3:]).max(axis=1), np.abs(gq[:, 3:] + out[1][0][:, 3:]).max(axis=1))
+    assert dq.max() < tol, dq.max()
+    # positions ~550 m up: one float ulp is 6e-5 and both paths round 256 times (the plane-frame rotation mixes y and z)
+    assert np.allclose(gq[:, :3], out[1][0][:, :3], rtol=0, atol=1e-9 if dtype == np.float64 else 5e-2)
