@@ -313,7 +313,7 @@ def b200_arm(args):
                             "reference layout)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp64" if args.dtype == "fp64" else "fp32", "kernel": ("rbs::step_sphere_plane_pf_kernel<double,6,COUNT=false,THR=false> (plane-frame fast kernel)" if args.arith == "fast" else "rbs::step_body_plane_kernel<double,sphere,schemeA,iso>") if args.dtype == "fp64" else "float instantiation of the same kernel",
+            "roofline": {"bound": "fp64" if args.dtype == "fp64" else "fp32", "kernel": ("rbs::step_sphere_plane_pf_kernel<double,6,COUNT=false,THR=false> (plane-frame fast kernel)" if args.arith == "fast" else "rbs::step_body_plane_kernel<double,sphere,schemeA,iso>") if args.dtype == "fp64" else ("rbs::step_sphere_plane_pf2_kernel<6,COUNT=false,THR=false> (plane-frame fast kernel, two envs per thread on packed fp32x2 FFMA2, branch-free contact path)" if args.arith == "fast" and os.environ.get("RBS_PF_PACKED", "1") != "0" else "float instantiation of the fp64 kernel"),
                          "achieved": fused_tflops, "peak": fp_peak, "unit": "TFLOP/s", "frac": fused_tflops / fp_peak,
                          "peak_source": "FMA microbenchmark rbs_fma_probe run in this process (MEASURED_PEAKS.json has no "
                                         "CUDA-core peak)",

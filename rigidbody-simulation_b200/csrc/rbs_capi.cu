@@ -172,6 +172,29 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
     static const int pf_min = [] { const char *e = getenv("RBS_PF_MIN_SUBSTEPS"); return e ? atoi(e) : 4; }();
     if (a->substeps >= pf_min && !a->trajectory) {   // fused launches: work in the plane frame (two rotations per launch pay off)
         const bool count = a->n_contacts || a->n_impulses, thr = a->contact_threshold > 0;
+        if constexpr (sizeof(T) == 4) {
+            // float: two environments per thread, packed fp32x2 arithmetic (bit-identical to the scalar kernel; the
+            // scalar one stays reachable with RBS_PF_PACKED=0 so that the tests can compare the two in one process)
+            const char *e = getenv("RBS_PF_PACKED");
+            if (!e || atoi(e) != 0) {
+                const unsigned grid2 = blocks_for(w.cnt, 2 * rbs::kBlock);
+#define RBS_PF2(COUNT, THR) rbs::step_sphere_plane_pf2_kernel<6, COUNT, THR><<<grid2, rbs::kBlock, 0, st>>>(p)
+                if (count) { if (thr) RBS_PF2(true, true); else RBS_PF2(true, false); }
+                else { if (thr) RBS_PF2(false, true); else RBS_PF2(false, false); }
+#undef RBS_PF2
+                return;
+            }
+        }
+        {   // experiment knob: the straight-line (branch-free contact path) form of the scalar kernel
+            const char *e = getenv("RBS_PF_BRANCHFREE");
+            if (e && atoi(e) != 0) {
+#define RBS_PFB(COUNT, THR) rbs::step_sphere_plane_pf_bf_kernel<T, 6, COUNT, THR><<<grid, rbs::kBlock, 0, st>>>(p)
+                if (count) { if (thr) RBS_PFB(true, true); else RBS_PFB(true, false); }
+                else { if (thr) RBS_PFB(false, true); else RBS_PFB(false, false); }
+#undef RBS_PFB
+                return;
+            }
+        }
         const bool wide = tuning_minb(a->substeps, RBS_ARITH_FAST) == 8;
 #define RBS_PF(MINB, COUNT, THR) rbs::step_sphere_plane_pf_kernel<T, MINB, COUNT, THR><<<grid, rbs::kBlock, 0, st>>>(p)
 #define RBS_PF_MINB(COUNT, THR) do { if (wide) RBS_PF(8, COUNT, THR); else RBS_PF(6, COUNT, THR); } while (0)

@@ -1111,3 +1111,33 @@ def test_fused_launch_survives_fast_spin(rb, dtype):
     assert dq.max() < tol, dq.max()
     # positions ~550 m up: one float ulp is 6e-5 and both paths round 256 times (the plane-frame rotation mixes y and z)
     assert np.allclose(gq[:, :3], out[1][0][:, :3], rtol=0, atol=1e-9 if dtype == np.float64 else 5e-2)
+
+
+def test_packed_float_kernel_matches_scalar_kernel(rb):
+    """Float fused launches run two environments per thread on packed fp32x2 instructions with a branch-free contact
+    path (step_sphere_plane_pf2_kernel).  Every environment goes through the scalar plane-frame kernel's operations
+    in the same order, so states and event counters must be the same numbers (RBS_PF_PACKED=0 selects the scalar
+    kernel): ragged sizes (odd, smaller than one CTA, not a multiple of 256), with and without counters / threshold,
+    over a horizon in which most environments bounce.  (The per-step bar against the oracle for this kernel is
+    test_plane_frame_kernel_arbitrary_plane[float32], whose fused launches take this path by default.)"""
+    from rigidbody_simulation_b200 import scenes, stepper, synth
+    dev = torch.device("cuda:0")
+    for E, thr, count in ((100_003, 0.0, True), (77, 1e-4, True), (65_536 + 129, 1e-4, False), (4096, 0.0, False)):
+        s = synth.sphere_incline(E)
+        res = {}
+        for packed in ("0", "1"):
+            os.environ["RBS_PF_PACKED"] = packed
+            try:
+                model = scenes.sphere_on_incline(E, device=dev, dtype=torch.float32)
+                model.set_per_env(restitution=s["restitution"], friction=s["friction"])
+                data = rb.BatchedData(model)
+                data.set_state(s["qpos"], s["qvel"])
+                for K in (4, 260, 37):
+                    stepper.step_body_plane(model, data, -1, s["dt"], None, None, thr, substeps=K, count=count, arith="fast")
+                res[packed] = state_of(data) + tuple(c.copy() for c in data.counters())
+            finally:
+                os.environ.pop("RBS_PF_PACKED", None)
+        for a, b in zip(res["0"], res["1"]):
+            assert np.array_equal(a, b), (E, thr, count, np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max())
+        if count:
+            assert res["1"][2].sum() > E // 2                      # the horizon does exercise contacts
