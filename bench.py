@@ -313,7 +313,7 @@ def b200_arm(args):
                             "reference layout)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp64" if args.dtype == "fp64" else "fp32", "kernel": ("rbs::step_sphere_plane_pf_kernel<double,6,COUNT=false,THR=false> (plane-frame fast kernel)" if args.arith == "fast" else "rbs::step_body_plane_kernel<double,sphere,schemeA,iso>") if args.dtype == "fp64" else ("rbs::step_sphere_plane_pf2_kernel<6,COUNT=false,THR=false> (plane-frame fast kernel, two envs per thread on packed fp32x2 FFMA2, branch-free contact path)" if args.arith == "fast" and os.environ.get("RBS_PF_PACKED", "1") != "0" else "float instantiation of the fp64 kernel"),
+            "roofline": {"bound": "fp64" if args.dtype == "fp64" else "fp32", "kernel": ("rbs::step_sphere_plane_pf_kernel<double,6,COUNT=false,THR=false,UNROLL=4> (plane-frame fast kernel)" if args.arith == "fast" else "rbs::step_body_plane_kernel<double,sphere,schemeA,iso>") if args.dtype == "fp64" else ("rbs::step_sphere_plane_pf2_kernel<6,COUNT=false,THR=false> (plane-frame fast kernel, two envs per thread on packed fp32x2 FFMA2, branch-free contact path)" if args.arith == "fast" and os.environ.get("RBS_PF_PACKED", "1") != "0" else "float instantiation of the fp64 kernel"),
                          "achieved": fused_tflops, "peak": fp_peak, "unit": "TFLOP/s", "frac": fused_tflops / fp_peak,
                          "peak_source": "FMA microbenchmark rbs_fma_probe run in this process (MEASURED_PEAKS.json has no "
                                         "CUDA-core peak)",
@@ -321,10 +321,10 @@ def b200_arm(args):
                          "impulses_per_env_substep": i_per, "launch_ms": launch_ms, "substeps_per_launch": F,
                          "hbm_GBps_of_same_launch": fused_gbs,
                          # dram__bytes_read.sum + dram__bytes_write.sum from the ncu --set full capture in
-                         # profiles/r1_ncu_full_pf_kernel.csv: 62.9 + 8.0 MB per half-batch launch, two launches per
+                         # profiles/r1_ncu_full_pf_kernel.csv: 62.9 + 7.7 MB per half-batch launch, two launches per
                          # advance of all envs (most of the 54.5 MB write-back is still in the 126 MB L2 when a launch
                          # ends).  Valid for the default 1,048,576-env fp64 shape only.
-                         "traffic": 141.9e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
+                         "traffic": 141.3e6 if (E == ENVS_PER_GPU and args.dtype == "fp64") else None},
             "roofline_k1": {"bound": "hbm", "kernel": "same kernel, 1 substep per launch (the reference's per-frame call)",
                             "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
                             "peak_source": hbm_src, "frac_of_nominal_8TBps": k1_gbs / 8000.0,

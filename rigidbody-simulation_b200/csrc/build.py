@@ -39,14 +39,18 @@ def build(force=False, verbose=False, extra=()):
     if not force and up_to_date():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ["-o", OUT] + SOURCES
+    tmp = OUT + ".building"                 # linked next to the target and renamed: a snapshot never sees half a library
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ["-o", tmp] + SOURCES
     env = dict(os.environ)
     # the image's CC wrapper is fine as nvcc's host compiler; keep PATH as is
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if verbose or r.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed building librbsim_b200.so")
+    os.replace(tmp, OUT)
     return OUT
 
 

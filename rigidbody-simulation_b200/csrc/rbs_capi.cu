@@ -79,6 +79,8 @@ template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_a
     p.thr = (T)a->contact_threshold;
     for (int i = 0; i < 3; ++i) p.gdt[i] = p.g[i] * p.dt;
     p.hdt = (T)0.5 * p.dt;
+    p.inv_hdt = (T)1 / p.hdt;
+    p.inv_dt = (T)0.5 * p.inv_hdt;
     {   // plane frame (double on the host): rows t1, t2, n; quaternion of that rotation; gravity*dt in the frame
         const double n[3] = {a->plane_normal[0], a->plane_normal[1], a->plane_normal[2]};
         double t1[3] = {0, 0, 0}, t2[3];
@@ -182,16 +184,6 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
                 if (count) { if (thr) RBS_PF2(true, true); else RBS_PF2(true, false); }
                 else { if (thr) RBS_PF2(false, true); else RBS_PF2(false, false); }
 #undef RBS_PF2
-                return;
-            }
-        }
-        {   // experiment knob: the straight-line (branch-free contact path) form of the scalar kernel
-            const char *e = getenv("RBS_PF_BRANCHFREE");
-            if (e && atoi(e) != 0) {
-#define RBS_PFB(COUNT, THR) rbs::step_sphere_plane_pf_bf_kernel<T, 6, COUNT, THR><<<grid, rbs::kBlock, 0, st>>>(p)
-                if (count) { if (thr) RBS_PFB(true, true); else RBS_PFB(true, false); }
-                else { if (thr) RBS_PFB(false, true); else RBS_PFB(false, false); }
-#undef RBS_PFB
                 return;
             }
         }
@@ -646,8 +638,15 @@ int rbs_step_two_ball(const rbs_two_ball_args *a) {
     const unsigned grid = blocks_for(a->n_env, rbs::kBlock);
     cudaStream_t st = as_stream(a->stream);
     if (a->arith == RBS_ARITH_FAST) {
-        if (a->dtype == RBS_F64) rbs::step_two_ball_fast_kernel<double><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a));
-        else rbs::step_two_ball_fast_kernel<float><<<grid, rbs::kBlock, 0, st>>>(make_params<float>(a));
+        // gravity along z only (every shipped model): the additions of +0.0 to the horizontal velocities are not issued
+        const bool gz = a->gravity[0] == 0.0 && a->gravity[1] == 0.0;
+        if (a->dtype == RBS_F64) {
+            if (gz) rbs::step_two_ball_fast_kernel<double, true><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a));
+            else rbs::step_two_ball_fast_kernel<double, false><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a));
+        } else {
+            if (gz) rbs::step_two_ball_fast_kernel<float, true><<<grid, rbs::kBlock, 0, st>>>(make_params<float>(a));
+            else rbs::step_two_ball_fast_kernel<float, false><<<grid, rbs::kBlock, 0, st>>>(make_params<float>(a));
+        }
     } else if (a->dtype == RBS_F64) {
         rbs::step_two_ball_kernel<double><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a));
     } else {

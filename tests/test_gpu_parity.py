@@ -1141,3 +1141,34 @@ def test_packed_float_kernel_matches_scalar_kernel(rb):
             assert np.array_equal(a, b), (E, thr, count, np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max())
         if count:
             assert res["1"][2].sum() > E // 2                      # the horizon does exercise contacts
+
+
+def test_two_ball_tilted_gravity_both_policies(rb):
+    """The two-ball fast kernel has a gravity-along-z instantiation (every shipped model) and a general one: a gravity
+    vector with horizontal components goes through the general one and must meet the same bar against the oracle;
+    the strict policy stays bit-for-bit."""
+    from rigidbody_simulation_b200 import stepper, synth
+    from rigidbody_simulation_b200.src.simulation import ball_collision
+    E = 20_000
+    s = synth.two_ball(E)
+    g = [0.7, -0.4, -9.8]
+    for arith in ("strict", "fast"):
+        model, data = ball_collision.build(E)
+        model.opt.gravity[:] = g
+        data.set_state(s["qpos"], s["qvel"])
+        qp, qv = s["qpos"].copy(), s["qvel"].copy()
+        hits = (np.zeros(E, np.uint32), np.zeros(E, np.uint32))
+        m = float(model.body_mass[1])
+        done = 0
+        for upto in (1, 120):
+            co.step_two_ball(qp, qv, upto - done, mass=[m, m], radius=0.1, gravity=g, dt=0.01, restitution=1.0, friction=0.3, counters=hits)
+            stepper.step_two_ball(model, data, 0.01, 1.0, 0.3, radius=0.1, substeps=upto - done, arith=arith)
+            done = upto
+            gq, gv = state_of(data)
+            err = max(comp_rel_err(gq, qp, 1e-3), comp_rel_err(gv, qv, 1e-3))
+            assert err <= (F64_STEP if upto == 1 else 1e-7), (arith, upto, err)
+            if arith == "strict":
+                assert err == 0.0
+        same = (data.n_contacts[:E].cpu().numpy() == hits[0]) & (data.n_impulses[:E].cpu().numpy() == hits[1])
+        assert same.mean() >= (1.0 if arith == "strict" else 0.9999), (arith, same.mean())
+        assert hits[0].sum() > 0 and hits[1].sum() > E // 2
