@@ -1172,3 +1172,46 @@ def test_two_ball_tilted_gravity_both_policies(rb):
         same = (data.n_contacts[:E].cpu().numpy() == hits[0]) & (data.n_impulses[:E].cpu().numpy() == hits[1])
         assert same.mean() >= (1.0 if arith == "strict" else 0.9999), (arith, same.mean())
         assert hits[0].sum() > 0 and hits[1].sum() > E // 2
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fused_fast_kernels_degenerate_inputs(rb, dtype):
+    """The fused fast sphere kernels decide `dist < 0`, `u_n < 0` and `|u_t| > 1e-6` with integer tests on the bit
+    patterns (double) or on packed pairs of environments (float).  Degenerate inputs must behave like the reference:
+    a sphere exactly touching at rest (dist == 0) is not in contact on the first substep, one resting exactly on the
+    plane with zero approach speed gets no impulse, a NaN environment stays NaN and does not disturb the environment
+    that shares its thread / warp, and the event counters equal the oracle's."""
+    from rigidbody_simulation_b200 import stepper
+    E = 300                                # not a multiple of 256: the packed kernel's second slot idles in the tail
+    qpos = np.tile(np.array([0, 0, 1.0, 1, 0, 0, 0.0]), (E, 1))
+    qvel = np.zeros((E, 6))
+    qpos[:, 2] = np.linspace(0.15, 0.6, E)                  # some start penetrating, some just above, most in the air
+    qvel[:, 2] = np.linspace(-1.0, 0.5, E)
+    qvel[:, 3] = 3.0
+    qpos[9, 2], qvel[9, 2] = 0.2, 0.0                       # exactly touching, at rest
+    qpos[10, 2], qvel[10, 2] = 0.2, -0.5                    # exactly touching, approaching: still dist == 0, no contact
+    qpos[11, 2], qvel[11, 2] = 0.1999, 0.0                  # penetrating, v_z becomes g*dt < 0 on the first substep
+    qpos[7, 2] = np.nan
+    qpos[7 + 128, 5] = np.nan                               # shares a thread with env 7 in the packed float kernel
+    model, data = make_single(rb, "sphere", [0.2], 0.0, qpos, qvel, dtype=dtype)
+    ok = np.ones(E, bool)
+    ok[[7, 7 + 128]] = False
+    qp, qv = qpos.astype(dtype), qvel.astype(dtype)
+    cnt = (np.zeros(E, np.uint32), np.zeros(E, np.uint32))
+    kw = dict(geom="sphere", mass=model.body_mass[-1], inertia=model.body_inertia[-1], size=0.2, plane_pos=[0, 0, 0],
+              plane_normal=[0, 0, 1], gravity=G, dt=0.009, restitution=0.8, friction=0.5, threshold=0.0, counters=cnt)
+    for K in (1, 4, 60):                   # 1: world-frame kernel; 4, 60: plane-frame kernels (packed in float)
+        co.step_body_plane(qp, qv, K, **kw)
+        stepper.step_body_plane(model, data, -1, 0.009, 0.8, 0.5, 0.0, substeps=K, arith="fast")
+        gq, gv = state_of(data)
+        if K == 1:
+            calls, _ = data.counters()
+            assert calls[9, 0] == 0 and calls[10, 0] == 0 and calls[11, 0] == 1
+        assert np.isnan(gq[7, 2]) and np.isnan(gq[7 + 128, 3:]).all()
+        assert np.isfinite(gq[ok]).all() and np.isfinite(gv[ok]).all()
+        if dtype == np.float64:
+            assert comp_rel_err(gq[ok], qp[ok], 1e-3) <= 1e-10 and comp_rel_err(gv[ok], qv[ok], 1e-3) <= 1e-10
+    calls, imps = data.counters()
+    if dtype == np.float64:
+        assert (calls[ok, 0] == cnt[0][ok]).all() and (imps[ok, 0] == cnt[1][ok]).all()
+    assert cnt[0][ok].sum() > 50
