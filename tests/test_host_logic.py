@@ -311,3 +311,43 @@ def test_checkpoint_round_trip_cpu(tmp_path):
     m3 = rb.BatchedModel.from_xml_path(scenes.model_path("sphere"), nenv=6, device="cpu")
     with pytest.raises(ValueError):
         rb.BatchedData(m3).load_state_dict(d.state_dict())
+
+
+def test_bit_pattern_comparisons_decide_like_the_fp_tests():
+    """rbs_kernels.cuh moves the always-executed comparisons of the fused double kernels off the FP64 pipe by comparing
+    bit patterns (below_nonneg, above_positive, clamp_to_minus_one, sign_bit).  NumPy restatement of those integer
+    tests against the floating-point tests they replace, over random and edge operands: they must agree everywhere
+    except the documented cases (x = -0.0 against y = +0.0; -0.0 under sign_bit; NaN)."""
+    rng = np.random.default_rng(11)
+    edge = np.array([0.0, -0.0, 5e-324, -5e-324, 2.2250738585072014e-308, -2.2250738585072014e-308, 1e-12, 1.0000000000000002e-12,
+                     9.999999999999998e-13, 1.0, -1.0, np.nextafter(-1.0, 0.0), np.nextafter(-1.0, -2.0), 0.2, np.nextafter(0.2, 1.0),
+                     np.nextafter(0.2, 0.0), 1e308, -1e308, np.inf, -np.inf])
+    x = np.concatenate([edge, rng.normal(size=20000) * 10.0 ** rng.integers(-300, 300, 20000), rng.uniform(-2, 2, 20000)])
+    bits = lambda a: np.asarray(a, np.float64).view(np.int64)
+    # below_nonneg(x, y) = x < y for y >= +0
+    for y in (0.0, 5e-324, 0.2, 1.0, 1e300, np.inf):
+        got = bits(x) < bits(np.float64(y))
+        want = x < y
+        differ = got != want
+        assert (differ <= ((x == 0) & np.signbit(x) & (y == 0.0))).all(), y      # only -0.0 against +0.0
+    # above_positive(x, c) = x > c for x >= 0, c > 0
+    xp = np.abs(x)
+    for c in (1e-12, 1e-16, 5e-324, 1.0):
+        assert ((bits(xp) > bits(np.float64(c))) == (xp > c)).all(), c
+    # clamp_to_minus_one(c) = c > -1 ? c : -1 for c <= 0: |c| < 1 read off the high word
+    xn = -np.abs(x)
+    hi = (bits(xn) >> 32) & 0x7FFFFFFF
+    got = np.where(hi < 0x3FF00000, xn, -1.0)
+    want = np.where(xn > -1.0, xn, -1.0)
+    assert np.array_equal(got, want)
+    nan_hi = (bits(np.float64(np.nan)) >> 32) & 0x7FFFFFFF
+    assert not (nan_hi < 0x3FF00000)                                             # NaN -> -1, like the FP test
+    # sign_bit(x) against !(x >= 0): differ only for -0.0
+    got = (bits(x) >> 32).astype(np.int32) < 0
+    want = ~(x >= 0)
+    assert ((got != want) <= ((x == 0) & np.signbit(x))).all()
+    # the float kernels keep the FP forms; the same identities hold for binary32 (used by nobody, checked for the record)
+    xf = x[np.abs(x) < 1e38].astype(np.float32)
+    fb = lambda a: np.asarray(a, np.float32).view(np.int32)
+    got, want = fb(xf) < fb(np.float32(0.2)), xf < np.float32(0.2)
+    assert np.array_equal(got, want)
