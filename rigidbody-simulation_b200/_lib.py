@@ -79,6 +79,8 @@ PROTOTYPES = {
     "rbs_last_error": (c_char_p, []),
     "rbs_launch_count": (c_ulonglong, []),
     "rbs_device_count": (c_int, []),
+    "rbs_set_option": (c_int, [c_char_p, c_long]),
+    "rbs_get_option": (c_long, [c_char_p]),
     "rbs_impulse_friction": (c_int, [c_int, c_long, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_double, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rbs_apply_impulse_friction": (c_int, [c_int, c_long, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p,
@@ -143,3 +145,18 @@ def check(rc):
 
 def launch_count():
     return int(load().rbs_launch_count())
+
+
+def set_option(name, value):
+    """Tuning knob of the launch dispatch (include/rbsim_b200.h: rbs_set_option); returns the previous value."""
+    lib = load()
+    old = int(lib.rbs_get_option(name.encode()))
+    check(lib.rbs_set_option(name.encode(), int(value)))
+    return old
+
+
+def get_option(name):
+    v = int(load().rbs_get_option(name.encode()))
+    if v == -(1 << 63):
+        raise ValueError(f"unknown option {name!r}")
+    return v

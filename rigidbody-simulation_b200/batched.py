@@ -242,6 +242,13 @@ class BatchedData:
         self.xfrc_applied = None if x is None else x.to(device=self.device, dtype=self.dtype).contiguous()
 
     def counters(self):
-        """(contacts handed to the impulse routine, impulses applied) per body, as int64 host arrays."""
-        return (self.n_contacts.cpu().numpy().astype(np.int64).reshape(self.nenv, self.nfree),
-                self.n_impulses.cpu().numpy().astype(np.int64).reshape(self.nenv, self.nfree))
+        """Event counters as int64 host arrays.
+
+        Single-body and multi-sphere steppers: (contacts handed to the impulse routine, impulses applied), one entry
+        per body, shape ``[nenv, nfree]``.  Two-ball stepper (env layout, two free bodies): the kernel counts per
+        ENVIRONMENT -- (ground hits of either ball, ball-ball hits), shape ``[nenv, 1]`` -- because
+        ``step_with_custom_collisions`` has no per-ball notion of a pair hit (ball_collision.py:103-118)."""
+        nc, ni = (t.cpu().numpy().astype(np.int64) for t in (self.n_contacts, self.n_impulses))
+        if self.layout == "env" and self.nfree > 1:
+            return nc[:self.nenv].reshape(self.nenv, 1), ni[:self.nenv].reshape(self.nenv, 1)
+        return nc.reshape(self.nenv, self.nfree), ni.reshape(self.nenv, self.nfree)

@@ -9,7 +9,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <climits>
 #include <cstdlib>
+#include <cstring>
 #include <cmath>
 #include <mutex>
 
@@ -34,6 +36,40 @@ int check_launch(const char *what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return RBS_OK;
 }
+
+// Tuning knobs (rbs_set_option / rbs_get_option).  Each starts from its environment variable, so a deployment can
+// still pin it from outside; tests and benchmarks flip them in-process.  None of them changes what is computed,
+// only which instantiation / launch shape computes it.
+struct Option {
+    const char *name, *env;
+    std::atomic<long> value;
+    long fallback;
+};
+Option g_options[] = {
+    {"minb", "RBS_MINB", {0}, 0},                            // resident CTAs per SM of the sphere steppers (0 = tuned default)
+    {"pf_min_substeps", "RBS_PF_MIN_SUBSTEPS", {0}, 4},      // shortest launch that takes the plane-frame kernels
+    {"pf_packed", "RBS_PF_PACKED", {0}, 1},                  // float sphere stepper: packed fp32x2 kernel (1) or scalar (0)
+    {"box_minb", "RBS_BOX_MINB", {0}, 6},                    // resident CTAs per SM of the plane-frame box kernel
+    {"box_compact", "RBS_BOX_COMPACT", {0}, 1},              // plane-frame box kernel: CTA-level compaction of contacts
+    {"ms_skin_percent", "RBS_MS_SKIN_PERCENT", {0}, 50},     // starting skin of the adaptive partner lists
+    {"ms_sorted", "RBS_MS_SORTED", {0}, 1},                  // multi-sphere fast kernel: contact-count-sorted impulse chains
+    {"probe_mode", "RBS_PROBE_MODE", {0}, 1},                // rbs_fma_probe operand mode
+    {"host_chunks", "RBS_HOST_CHUNKS", {0}, 16},             // pipeline depth of rbs_run_body_plane_host
+};
+std::once_flag g_options_once;
+Option *find_option(const char *name) {
+    std::call_once(g_options_once, [] {
+        for (Option &o : g_options) {
+            const char *e = getenv(o.env);
+            o.value.store(e ? atol(e) : o.fallback, std::memory_order_relaxed);
+        }
+    });
+    if (!name) return nullptr;
+    for (Option &o : g_options)
+        if (strcmp(o.name, name) == 0) return &o;
+    return nullptr;
+}
+inline long option(const char *name) { return find_option(name)->value.load(std::memory_order_relaxed); }
 
 inline unsigned blocks_for(long n, int block) { return (unsigned)((n + block - 1) / block); }
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -134,7 +170,7 @@ template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_a
 // the one-substep streaming launch at 8 (64 regs, more loads in flight); fast policy -- 6 (79 regs, no spills) for both.
 // RBS_MINB overrides for experiments.
 int tuning_minb(int substeps, int arith) {
-    static int forced = [] { const char *e = getenv("RBS_MINB"); return e ? atoi(e) : 0; }();
+    const int forced = (int)option("minb");
     if (forced) return forced;
     if (arith == RBS_ARITH_FAST) return 6;
     return substeps <= 2 ? 8 : 6;
@@ -171,14 +207,12 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
         rbs::step_sphere_plane_fast_kernel<T, 4, true><<<grid, rbs::kBlock, 0, st>>>(p);
         return;
     }
-    static const int pf_min = [] { const char *e = getenv("RBS_PF_MIN_SUBSTEPS"); return e ? atoi(e) : 4; }();
-    if (a->substeps >= pf_min && !a->trajectory) {   // fused launches: work in the plane frame (two rotations per launch pay off)
+    if (a->substeps >= option("pf_min_substeps") && !a->trajectory) {   // fused launches: work in the plane frame (two rotations per launch pay off)
         const bool count = a->n_contacts || a->n_impulses, thr = a->contact_threshold > 0;
         if constexpr (sizeof(T) == 4) {
             // float: two environments per thread, packed fp32x2 arithmetic (bit-identical to the scalar kernel; the
             // scalar one stays reachable with RBS_PF_PACKED=0 so that the tests can compare the two in one process)
-            const char *e = getenv("RBS_PF_PACKED");
-            if (!e || atoi(e) != 0) {
+            if (option("pf_packed") != 0) {
                 const unsigned grid2 = blocks_for(w.cnt, 2 * rbs::kBlock);
 #define RBS_PF2(COUNT, THR) rbs::step_sphere_plane_pf2_kernel<6, COUNT, THR><<<grid2, rbs::kBlock, 0, st>>>(p)
                 if (count) { if (thr) RBS_PF2(true, true); else RBS_PF2(true, false); }
@@ -206,11 +240,10 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
 
 template <typename T> void launch_box_plane_fast(const rbs_body_plane_args *a, const Window &w) {
     const rbs::BodyPlaneParams<T> p = make_params<T>(a, w);
-    static const int pf_min = [] { const char *e = getenv("RBS_PF_MIN_SUBSTEPS"); return e ? atoi(e) : 4; }();
-    if (!a->xfrc && !a->trajectory && a->substeps >= pf_min) {   // fused launches: plane frame (two rotations per launch pay off)
+    if (!a->xfrc && !a->trajectory && a->substeps >= option("pf_min_substeps")) {   // fused launches: plane frame (two rotations per launch pay off)
         // resident CTAs per SM (register cap 128 / 96 / 80); measured on B200, 1M cubes fp64, 128 fused substeps:
         // 6.14e10 / 6.49e10 / 6.55e10 env-substeps/s bouncing, 4.39e10 / 4.63e10 / 4.69e10 sliding on the incline
-        static const int minb = [] { const char *e = getenv("RBS_BOX_MINB"); return e ? atoi(e) : 6; }();
+        const int minb = (int)option("box_minb");
         const unsigned grid = blocks_for(w.cnt, rbs::kBlock);
         switch (minb) {
             case 4: rbs::step_box_plane_pf_kernel<T, 4><<<grid, rbs::kBlock, 0, w.stream>>>(p); break;
@@ -326,7 +359,7 @@ template <typename T> rbs::MultiSphereParams<T> make_params(const rbs_multi_sphe
     p.hdt = (T)0.5 * p.dt;
     // 0 = adaptive per CTA, starting at 50 % (or at RBS_MS_SKIN_PERCENT); > 0 = pinned; < 0 = no lists.  A launch of
     // fewer than 4 substeps (the reference's per-frame call) cannot amortise a list and scans every substep.
-    static const int default_skin = [] { const char *e = getenv("RBS_MS_SKIN_PERCENT"); const int v = e ? atoi(e) : 50; return v > 0 ? v : 50; }();
+    const int default_skin = option("ms_skin_percent") > 0 ? (int)option("ms_skin_percent") : 50;
     int skin_pct = a->list_skin_percent != 0 ? a->list_skin_percent : default_skin;
     if (a->list_skin_percent == 0 && a->substeps < 4) skin_pct = -1;
     p.skin = skin_pct > 0 ? (T)(skin_pct * 0.01) : T(0);
@@ -355,7 +388,7 @@ int validate_multi_sphere(const rbs_multi_sphere_args *a, bool need_state) {
     return RBS_OK;
 }
 
-template <typename T> void launch_multi_sphere(const rbs_multi_sphere_args *a) {
+template <typename T> int launch_multi_sphere(const rbs_multi_sphere_args *a) {
     const int B = a->n_body;
     int threads = ((B + 31) / 32) * 32;
     if (threads < 128) threads = 128;
@@ -367,12 +400,16 @@ template <typename T> void launch_multi_sphere(const rbs_multi_sphere_args *a) {
                         (size_t)((B + 63) / 64) * threads * sizeof(unsigned long long);
     cudaStream_t st = as_stream(a->stream);
     const bool iso = a->inertia_mode == RBS_INERTIA_ISOTROPIC;
-    // above 48 KB (B > ~450) the dynamic shared memory needs the opt-in attribute; set it once per instantiation
+    // above 48 KB (B > ~450) the dynamic shared memory needs the opt-in attribute.  It is a property of the function on
+    // the CURRENT device, so it is set on every such launch (cheap) rather than remembered per process.
 #define RBS_MS_LAUNCH(KERNEL)                                                                                   \
     do {                                                                                                        \
-        static size_t allowed = 48 * 1024;                                                                      \
-        if (smem > allowed) {                                                                                   \
-            if (cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) allowed = smem; \
+        if (smem > 48 * 1024) {                                                                                 \
+            const cudaError_t e__ = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e__ != cudaSuccess) {                                                                           \
+                cudaGetLastError();                                                                             \
+                return fail(RBS_ECUDA, "rbs_step_multi_sphere: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e__)); \
+            }                                                                                                   \
         }                                                                                                       \
         KERNEL<<<grid, threads, smem, st>>>(p);                                                                 \
     } while (0)
@@ -380,7 +417,7 @@ template <typename T> void launch_multi_sphere(const rbs_multi_sphere_args *a) {
         if (threads <= 256) RBS_MS_LAUNCH((rbs::step_multi_sphere_fast_kernel<T, 256>));
         else if (threads <= 512) RBS_MS_LAUNCH((rbs::step_multi_sphere_fast_kernel<T, 512>));
         else RBS_MS_LAUNCH((rbs::step_multi_sphere_fast_kernel<T, 1024>));
-        return;
+        return RBS_OK;
     }
     if (threads <= 256) {
         if (iso) RBS_MS_LAUNCH((rbs::step_multi_sphere_kernel<T, 1, 256>));
@@ -393,6 +430,7 @@ template <typename T> void launch_multi_sphere(const rbs_multi_sphere_args *a) {
         else RBS_MS_LAUNCH((rbs::step_multi_sphere_kernel<T, 0, 1024>));
     }
 #undef RBS_MS_LAUNCH
+    return RBS_OK;
 }
 
 // cached device workspace of the host-buffer drivers -------------------------------------------
@@ -513,6 +551,22 @@ extern "C" {
 int rbs_version(void) { return RBS_ABI_VERSION; }
 const char *rbs_last_error(void) { return g_err; }
 unsigned long long rbs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int rbs_set_option(const char *name, long value) {
+    Option *o = find_option(name);
+    if (!o) return fail(RBS_EINVAL, "rbs_set_option: unknown option '%s'", name ? name : "(null)");
+    o->value.store(value, std::memory_order_relaxed);
+    return RBS_OK;
+}
+
+long rbs_get_option(const char *name) {
+    Option *o = find_option(name);
+    if (!o) {
+        fail(RBS_EINVAL, "rbs_get_option: unknown option '%s'", name ? name : "(null)");
+        return LONG_MIN;
+    }
+    return o->value.load(std::memory_order_relaxed);
+}
 
 int rbs_device_count(void) {
     int n = 0;
@@ -659,8 +713,8 @@ int rbs_step_multi_sphere(const rbs_multi_sphere_args *a) {
     int rc = validate_multi_sphere(a, true);
     if (rc) return rc;
     if (a->n_env == 0) return RBS_OK;
-    if (a->dtype == RBS_F64) launch_multi_sphere<double>(a);
-    else launch_multi_sphere<float>(a);
+    rc = a->dtype == RBS_F64 ? launch_multi_sphere<double>(a) : launch_multi_sphere<float>(a);
+    if (rc) return rc;
     return check_launch("rbs_step_multi_sphere");
 }
 
@@ -831,7 +885,7 @@ int rbs_fma_probe(int dtype, long n_threads, int iters, void *sink, void *stream
     if (bad_dtype(dtype)) return fail(RBS_EINVAL, "rbs_fma_probe: bad dtype %d", dtype);
     if (n_threads <= 0 || n_threads % 256 || iters < 1 || !sink) return fail(RBS_EINVAL, "rbs_fma_probe: n_threads must be a positive multiple of 256");
     const unsigned grid = (unsigned)(n_threads / 256);
-    static int mode = [] { const char *e = getenv("RBS_PROBE_MODE"); return e ? atoi(e) : 1; }();
+    const int mode = (int)option("probe_mode");
     cudaStream_t st = as_stream(stream);
     if (dtype == RBS_F64) {
         if (mode == 0) rbs::fma_probe_kernel<double, 0><<<grid, 256, 0, st>>>(iters, (double *)sink, 0.999999, 1e-7);

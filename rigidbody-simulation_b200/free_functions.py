@@ -52,9 +52,12 @@ class _Batch:
         return t
 
     def scalar(self, x):
-        """python scalar -> (NULL, value); array of n -> (device pointer, 0.0)."""
+        """python scalar or one-element array -> (NULL, value); array of n -> (device pointer, 0.0).  A per-item array
+        must have exactly as many entries as the batch (the kernels index it with the work-item index)."""
         if torch.is_tensor(x) and x.dim() > 0 or isinstance(x, np.ndarray) and x.ndim > 0:
             t = torch.as_tensor(x).to(device=self.device, dtype=self.dtype).contiguous().reshape(-1)
+            if t.numel() == 1:                       # uniform value in array clothing: never hand out a 1-element pointer
+                return None, float(t.item())
             self.batched = True
             self._size(t.shape[0])
             self.keep.append(t)

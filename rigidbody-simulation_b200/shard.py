@@ -67,3 +67,87 @@ def max_over_ranks(value, device):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin the calling thread (and every thread it starts afterwards) to the CPUs of the NUMA node that GPU
+    ``device_index`` hangs off, so that pinned host buffers allocated from now on are first-touched in the memory next
+    to that GPU's PCIe root.  With eight ranks streaming state in and out of one host this keeps each rank's H2D / D2H
+    traffic off the inter-socket link.  Best effort: returns what was done (for the bench line) and never raises."""
+    import os
+    info = {"bound": False}
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        info["pci"] = bdf
+        with open(base + "/numa_node") as f:
+            info["numa_node"] = int(f.read().strip())
+        with open(base + "/local_cpulist") as f:
+            local = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = local & allowed
+        info["allowed_cpus"] = len(allowed)
+        if info["numa_node"] < 0 or not cpus or cpus == allowed:
+            info["note"] = "single NUMA domain (or no locality information): nothing to bind"
+            return info
+        os.sched_setaffinity(0, cpus)
+        info.update(bound=True, cpus=len(cpus))
+    except Exception as exc:                       # sysfs not mounted, odd container: report and carry on unbound
+        info["note"] = "not bound: %r" % (exc,)
+    return info
+
+
+def host_link_bandwidth(device, pinned, world_size=1, rank=0, reps=4):
+    """Measured pinned-host <-> device copy bandwidth of every rank (GB/s, CUDA events): each rank ALONE (the others
+    idle at a barrier) and all ranks TOGETHER -- the figure that says whether the host-buffer path of an N-GPU job is
+    limited by this GPU's link or by what the host can feed to all of them at once."""
+    dev_buf = torch.empty(pinned.shape, dtype=pinned.dtype, device=device)
+    nbytes = pinned.numel() * pinned.element_size()
+
+    def measure():
+        out = []
+        for src, dst in ((pinned, dev_buf), (dev_buf, pinned)):
+            dst.copy_(src, non_blocking=True)                       # warm
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                dst.copy_(src, non_blocking=True)
+            b.record()
+            b.synchronize()
+            out.append(reps * nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
+        return out
+
+    multi = dist.is_available() and dist.is_initialized() and world_size > 1
+    alone = [0.0, 0.0]
+    for r in range(world_size):
+        if multi:
+            torch.cuda.synchronize(device)
+            dist.barrier()
+        if r == rank:
+            alone = measure()
+    together = alone
+    if multi:
+        torch.cuda.synchronize(device)
+        dist.barrier()
+        together = measure()
+        t = torch.tensor(alone + together, dtype=torch.float64, device=device)
+        rows = [torch.empty_like(t) for _ in range(world_size)]
+        dist.all_gather(rows, t)
+        table = [r.tolist() for r in rows]
+    else:
+        table = [alone + together]
+    return {"bytes_per_copy": nbytes, "unit": "GB/s",
+            "h2d_alone": [round(r[0], 2) for r in table], "d2h_alone": [round(r[1], 2) for r in table],
+            "h2d_all_ranks_together": [round(r[2], 2) for r in table], "d2h_all_ranks_together": [round(r[3], 2) for r in table],
+            "aggregate_together": round(sum(r[2] + r[3] for r in table), 1)}

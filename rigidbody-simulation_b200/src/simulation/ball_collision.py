@@ -50,10 +50,13 @@ def ball_collision_step(model, data, dt):
     return None                                              # two separate logs in the reference (:146-154)
 
 
-def run_headless(steps=500, nenv=1, device=None, dtype=torch.float64, substeps=1):
+def run_headless(steps=500, nenv=1, device=None, dtype=torch.float64, substeps=1, arith="strict"):
     model, data = build(nenv, device, dtype)
-    for _ in range(steps // substeps):
-        step_with_custom_collisions(model, data, model.opt.timestep, substeps=substeps)
+    done = 0
+    while done < steps:                                     # launches of `substeps`, ragged last one
+        k = min(substeps, steps - done)
+        step_with_custom_collisions(model, data, model.opt.timestep, substeps=k, arith=arith)
+        done += k
     return model, data, None
 
 

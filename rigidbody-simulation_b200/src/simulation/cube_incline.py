@@ -3,6 +3,8 @@
 ``load_sim_config("cube_incline")`` (:14), ``models/cube.xml`` (:33-42), cube from rest (:46), step wrapper with
 ``timestep_integration`` passing dt, restitution and friction but NOT the threshold, so its default 1e-4 applies
 (:70-78)."""
+import functools
+
 import numpy as np
 import torch
 
@@ -30,15 +32,16 @@ def build(nenv=1, device=None, dtype=torch.float64):
     return model, data
 
 
-def cube_incline_step(model, data, dt, substeps=1, trajectory=None):
+def cube_incline_step(model, data, dt, substeps=1, trajectory=None, arith="strict"):
     return timestep_integration(model, obj, data, dt=dt, restitution=restitution, friction_coeff=friction_coefficient,
-                                substeps=substeps, trajectory=trajectory)
+                                substeps=substeps, trajectory=trajectory, arith=arith)
 
 
-def run_headless(steps=240, nenv=1, device=None, dtype=torch.float64, log=True, substeps_per_launch=1):
+def run_headless(steps=240, nenv=1, device=None, dtype=torch.float64, log=True, substeps_per_launch=1, arith="strict"):
     model, data = build(nenv, device, dtype)
     logger = TrajectoryLog(steps, min(nenv, 4), model.device, dtype) if log else None
-    start_main_loop(model, data, cube_incline_step, steps, logger, substeps_per_launch)
+    step = cube_incline_step if arith == "strict" else functools.partial(cube_incline_step, arith=arith)
+    start_main_loop(model, data, step, steps, logger, substeps_per_launch)
     if logger is not None:
         logger.finish()
     return model, data, logger

@@ -42,10 +42,13 @@ def custom_step_multi_sphere(model, data, dt=timestep, restitution=restitution_c
     return None
 
 
-def run_headless(steps=300, nenv=1, device=None, dtype=torch.float64, substeps=1, n_body=None):
+def run_headless(steps=300, nenv=1, device=None, dtype=torch.float64, substeps=1, n_body=None, arith="strict"):
     model, data = build(nenv, device, dtype, n_body)
-    for _ in range(steps // substeps):
-        custom_step_multi_sphere(model, data, model.opt.timestep, substeps=substeps)
+    done = 0
+    while done < steps:                                     # launches of `substeps`, ragged last one
+        k = min(substeps, steps - done)
+        custom_step_multi_sphere(model, data, model.opt.timestep, substeps=k, arith=arith)
+        done += k
     return model, data, None
 
 

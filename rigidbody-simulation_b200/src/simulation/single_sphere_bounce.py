@@ -4,6 +4,8 @@ Same configuration sources (``load_sim_config("single_sphere_bounce")`` :14, ``m
 ``{INCLINE_ANGLE}`` / ``{TIMESTEP}`` templating :26-36), same initial conditions (zero linear velocity, spin
 (2, 2, 0), :40-41), same step wrapper (:65-70, including obj="sphere", which is not a body of the scene: the
 lookup returns -1 and selects the last body, as shipped).  Window, video and plots are out of scope."""
+import functools
+
 import numpy as np
 import torch
 
@@ -34,16 +36,17 @@ def build(nenv=1, device=None, dtype=torch.float64):
     return model, data
 
 
-def sphere_simulation_step(model, data, dt, substeps=1, trajectory=None):
+def sphere_simulation_step(model, data, dt, substeps=1, trajectory=None, arith="strict"):
     return custom_step_with_impulse_collision_friction(model, "sphere", data, dt=dt, restitution=restitution,
                                                        friction_coeff=friction_coefficient, substeps=substeps,
-                                                       trajectory=trajectory)
+                                                       trajectory=trajectory, arith=arith)
 
 
-def run_headless(steps=2000, nenv=1, device=None, dtype=torch.float64, log=True, substeps_per_launch=1):
+def run_headless(steps=2000, nenv=1, device=None, dtype=torch.float64, log=True, substeps_per_launch=1, arith="strict"):
     model, data = build(nenv, device, dtype)
     logger = TrajectoryLog(steps, min(nenv, 4), model.device, dtype) if log else None
-    start_main_loop(model, data, sphere_simulation_step, steps, logger, substeps_per_launch)
+    step = sphere_simulation_step if arith == "strict" else functools.partial(sphere_simulation_step, arith=arith)
+    start_main_loop(model, data, step, steps, logger, substeps_per_launch)
     if logger is not None:
         logger.finish()
     return model, data, logger

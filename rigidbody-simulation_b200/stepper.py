@@ -124,12 +124,31 @@ def body_plane_args(model, data, body_id, dt, restitution, friction_coeff, conta
 
 
 def _key_of(value):
-    """cache key of a scalar-or-per-env argument: tensors by storage address (they are kept alive by the cached struct)"""
+    """cache key of a scalar-or-per-env argument.  Only DEVICE tensors are cacheable (by storage address; the cached
+    struct keeps them alive): a host tensor / array is uploaded on every call, so an in-place edit of it is seen."""
     if torch.is_tensor(value):
-        return ("t", value.data_ptr(), value.numel())
+        return ("t", value.data_ptr(), value.numel()) if value.device.type == "cuda" else None
     if isinstance(value, np.ndarray) and value.ndim > 0:
-        return None                                   # host arrays are uploaded on every call: not cacheable
+        return None
     return value
+
+
+def _refresh_by_value(a, model, dt, contact_threshold, strict_inertia, arith):
+    """The by-value fields of a cached struct are rewritten on every call (they are cheap), so MuJoCo-style edits of
+    the model between two steps -- ``model.opt.gravity[:] = ...``, ``model.body_mass[i] = ...`` -- take effect."""
+    bid = model.free_ids[0]
+    a.mass_u = float(model.body_mass[bid])
+    a.inertia_u = _lib.D3(*[float(v) for v in model.body_inertia[bid]])
+    a.size_u = _lib.D3(*[float(v) for v in model.body_geom[bid].size])
+    a.plane_point = _lib.D3(*model.plane_point)
+    a.plane_normal = _lib.D3(*model.plane_normal)
+    a.gravity = _lib.D3(*[float(g) for g in model.opt.gravity])
+    a.dt = float(dt)
+    a.contact_threshold = float(contact_threshold)
+    if strict_inertia is None:
+        strict_inertia = arith == "strict"
+    iso = model.per_env.get("inertia") is None and _isotropic(model.body_inertia[bid]) and not strict_inertia
+    a.inertia_mode = RBS_INERTIA_ISOTROPIC if iso else RBS_INERTIA_GENERAL
 
 
 def step_body_plane(model, data, body_id, dt, restitution, friction_coeff, contact_threshold,
@@ -139,12 +158,13 @@ def step_body_plane(model, data, body_id, dt, restitution, friction_coeff, conta
     (scheme A + isotropic inertia only; <= 1e-12 relative per step in fp64).
 
     The marshalled argument struct is cached per call signature and per identity of every device buffer it points to,
-    so a per-frame loop pays for one ctypes call per step, not for rebuilding 30 fields."""
+    so a per-frame loop pays for one ctypes call per step, not for rebuilding 30 fields.  Only pointers are trusted
+    from the cache: every by-value field is refreshed from the model on each call (_refresh_by_value)."""
     kr, kf = _key_of(restitution), _key_of(friction_coeff)
     a = None
     if not (kr is None and restitution is not None) and not (kf is None and friction_coeff is not None):
         pe = model.per_env
-        key = (body_id, dt, kr, kf, contact_threshold, scheme, count, strict_inertia, arith, env_range, data.state.data_ptr(),
+        key = (body_id, kr, kf, scheme, count, arith, env_range, data.state.data_ptr(),
                None if data.xfrc_applied is None else data.xfrc_applied.data_ptr(),
                tuple((k, t.data_ptr()) for k, t in pe.items()))
         cache = data.__dict__.setdefault("_args_cache", {})
@@ -154,6 +174,13 @@ def step_body_plane(model, data, body_id, dt, restitution, friction_coeff, conta
                 cache.clear()
             a = cache[key] = body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold,
                                              scheme, substeps, count, strict_inertia, arith, env_range)
+        else:
+            _refresh_by_value(a, model, dt, contact_threshold, strict_inertia, arith)
+            # python scalars for restitution / friction are by-value fields too (a tensor key pins the pointer)
+            if a.restitution is None and restitution is not None:
+                a.restitution_u = float(restitution)
+            if a.friction is None and friction_coeff is not None:
+                a.friction_u = float(friction_coeff)
         a.substeps = int(substeps)
     if a is None:
         a = body_plane_args(model, data, body_id, dt, restitution, friction_coeff, contact_threshold, scheme, substeps,
@@ -313,20 +340,22 @@ def run_body_plane_host(model, qpos, qvel, total_steps, body_id=-1, dt=None, res
                                                    _host_ptr(qvel, model.dtype, (E, 6)), int(total_steps)))
 
 
-def run_two_ball_host(model, qpos, qvel, total_steps, dt=None, restitution=1.0, friction=0.3, radius=0.1, substeps=32):
+def run_two_ball_host(model, qpos, qvel, total_steps, dt=None, restitution=1.0, friction=0.3, radius=0.1, substeps=32,
+                      arith="strict"):
     data = _HostShim(model, 2)
     a = two_ball_args(model, data, model.opt.timestep if dt is None else dt, restitution, friction, radius, substeps,
-                      count=False)
+                      count=False, arith=arith)
     a.stream = current_stream(model.device)
     E = model.nenv
     _lib.check(_lib.load().rbs_run_two_ball_host(ctypes.byref(a), _host_ptr(qpos, model.dtype, (E, 14)),
                                                  _host_ptr(qvel, model.dtype, (E, 12)), int(total_steps)))
 
 
-def run_multi_sphere_host(model, qpos, qvel, total_steps, dt=None, restitution=1.0, friction=0.0, substeps=8):
+def run_multi_sphere_host(model, qpos, qvel, total_steps, dt=None, restitution=1.0, friction=0.0, substeps=8,
+                          arith="strict"):
     data = _HostShim(model, model.nfree, layout="body")
     a = multi_sphere_args(model, data, model.opt.timestep if dt is None else dt, restitution, friction, substeps,
-                          count=False)
+                          count=False, arith=arith)
     a.stream = current_stream(model.device)
     E, B = model.nenv, model.nfree
     _lib.check(_lib.load().rbs_run_multi_sphere_host(ctypes.byref(a), _host_ptr(qpos, model.dtype, (E, 7 * B)),
@@ -362,6 +391,6 @@ def fma_peak(device, dtype=torch.float64, iters=4096, blocks_per_sm=8):
         _lib.check(lib.rbs_fma_probe(code, n_threads, iters, _ptr(sink), stream))
         t1.record()
         t1.synchronize()
-        chains = 16 if os.environ.get("RBS_PROBE_MODE") == "2" else 8
+        chains = 16 if _lib.get_option("probe_mode") == 2 else 8
         best = max(best, 2.0 * chains * n_threads * iters / (t0.elapsed_time(t1) * 1e-3))
     return best

@@ -1,0 +1,169 @@
+"""Parity of EXACTLY what bench.py times (run on the B200 box with ``-m gpu``).
+
+bench.py's headline number comes from ``step_sphere_plane_pf_kernel<double, 6, COUNT=false, THR=false, 4>`` (fp32:
+``step_sphere_plane_pf2_kernel<6, false, false>``): BASELINE configs[1], 1,048,576 environments, fast policy,
+``count=False``, launches of 256 fused substeps through ``stepper.SplitChains``, 2048 substeps per step.  The tests
+below drive that instantiation -- same sizes, same launch schedule -- against the C oracle
+(``oracle/rb_oracle.c``: the restatement of src/physics/collision.py:56-102 pinned to the reference's golden vectors):
+
+  * one substep from the same state through the plane-frame kernel itself: <= 1e-12 (fp64) / <= 1e-5 (fp32);
+  * divergence from the oracle at substeps 1 / 10 / 100 / 1000 / 2048 (reported; written to gpurun_out/ when present);
+  * the bench schedule (8 x 256 on two chains) with ``count=False`` and with ``count=True`` gives the same bits, and
+    the counters of the counted run equal the oracle's over the whole 2048-substep horizon (fp64).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import c_oracle as co
+from helpers import comp_rel_err
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = [0.0, 0.0, -9.8]
+E_BENCH, HORIZON, FUSE = 1 << 20, 2048, 256
+
+
+@pytest.fixture(scope="module")
+def rb():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import rigidbody_simulation_b200 as rb_
+    rb_._lib.load()
+    return rb_
+
+
+def _scene(rb, s, E, dtype):
+    from rigidbody_simulation_b200 import scenes
+    model = scenes.sphere_on_incline(E, device="cuda:0", dtype=torch.float64 if dtype == np.float64 else torch.float32)
+    model.set_per_env(restitution=s["restitution"], friction=s["friction"])
+    data = rb.BatchedData(model)
+    data.set_state(s["qpos"], s["qvel"])
+    return model, data
+
+
+def _state(data):
+    return (data.qpos.torch().cpu().numpy().astype(np.float64), data.qvel.torch().cpu().numpy().astype(np.float64))
+
+
+def _chained(chains, s, total, count):
+    """``total`` substeps in launches of at most FUSE through the two half-batch chains, as bench.py's one_step does"""
+    chains.fork()
+    done = 0
+    while done < total:
+        k = min(FUSE, total - done)
+        chains.step(dt=s["dt"], restitution=None, friction_coeff=None, contact_threshold=0.0, substeps=k, count=count,
+                    arith="fast")
+        done += k
+    chains.join()
+    torch.cuda.synchronize()
+
+
+def _row_err(g, r, floor):
+    """per-environment max over components of |g - r| / max(|r|, floor)"""
+    return np.max(np.abs(g - r) / np.maximum(np.abs(r), floor), axis=1)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+def test_headline_instantiation_1m_envs_2048_substeps_vs_oracle(rb, dtype, tol):
+    from rigidbody_simulation_b200 import stepper, synth
+    E = E_BENCH
+    s = synth.sphere_incline(E)
+    floor = 1e-3 if dtype == np.float64 else 1e-2
+    qp, qv = s["qpos"].astype(dtype), s["qvel"].astype(dtype)
+    cnt = (np.zeros(E, np.uint32), np.zeros(E, np.uint32))
+    model, data = _scene(rb, s, E, dtype)
+    okw = dict(geom="sphere", mass=model.body_mass[-1], inertia=model.body_inertia[-1], size=0.2, plane_pos=[0, 0, 0],
+               plane_normal=model.plane_normal, gravity=G, dt=s["dt"], restitution=s["restitution"], friction=s["friction"],
+               threshold=0.0, counters=cnt)
+
+    # (1) divergence curve; every launch -- also the 1-substep one -- goes through the plane-frame kernel
+    chains = stepper.SplitChains(model, data, parts=2)
+    old = rb._lib.set_option("pf_min_substeps", 1)
+    report = {"envs": E, "dtype": np.dtype(dtype).name, "kernel": "step_sphere_plane_pf_kernel<double,6,false,false,4>" if
+              dtype == np.float64 else "step_sphere_plane_pf2_kernel<6,false,false>", "checkpoints": {}}
+    try:
+        done = 0
+        for upto in (1, 10, 100, 1000, HORIZON):
+            co.step_body_plane(qp, qv, upto - done, **okw)
+            _chained(chains, s, upto - done, count=False)
+            done = upto
+            gq, gv = _state(data)
+            err = np.maximum(_row_err(gq, qp.astype(np.float64), floor), _row_err(gv, qv.astype(np.float64), floor))
+            report["checkpoints"][upto] = {"max": float(err.max()), "p50": float(np.median(err)), "p99": float(np.quantile(err, 0.99)),
+                                           "p99.99": float(np.quantile(err, 0.9999)),
+                                           "frac_above_1e-6": float(np.mean(err > 1e-6))}
+            assert np.isfinite(gq).all() and np.isfinite(gv).all()
+            if upto == 1:
+                assert err.max() <= tol, report
+            if upto == 10 and dtype == np.float64:
+                assert err.max() <= 1e-10, report
+    finally:
+        rb._lib.set_option("pf_min_substeps", old)
+    qn = np.sqrt((gq[:, 3:7] ** 2).sum(axis=1))
+    assert np.abs(qn - 1).max() < (1e-13 if dtype == np.float64 else 1e-5)
+    if dtype == np.float64:
+        assert report["checkpoints"][100]["p99"] <= 1e-8, report          # chaos amplifies, rounding does not explode
+
+    # (2) the bench schedule itself: 8 launches of 256 per chain, count=False -- then again with counters
+    data.set_state(s["qpos"], s["qvel"])
+    before = rb.launch_count()
+    _chained(chains, s, HORIZON, count=False)
+    assert rb.launch_count() - before == 2 * (HORIZON // FUSE)
+    uncounted = data.state.clone()
+    data.set_state(s["qpos"], s["qvel"])
+    data.n_contacts.zero_()
+    data.n_impulses.zero_()
+    _chained(chains, s, HORIZON, count=True)
+    assert torch.equal(data.state, uncounted)                 # COUNT=false and COUNT=true instantiations: same bits
+    calls, imps = data.counters()
+    mismatch = (calls[:, 0] != cnt[0]) | (imps[:, 0] != cnt[1])
+    report["bench_schedule"] = {"launches": 2 * (HORIZON // FUSE), "count_false_equals_count_true_bitwise": True,
+                                "oracle_contacts": int(cnt[0].sum()), "oracle_impulses": int(cnt[1].sum()),
+                                "gpu_contacts": int(calls.sum()), "gpu_impulses": int(imps.sum()),
+                                "envs_with_differing_counts": int(mismatch.sum())}
+    gq, gv = _state(data)
+    err = np.maximum(_row_err(gq, qp.astype(np.float64), floor), _row_err(gv, qv.astype(np.float64), floor))
+    report["bench_schedule"]["state_vs_oracle_at_2048"] = {"p50": float(np.median(err)), "p99": float(np.quantile(err, 0.99)),
+                                                           "max": float(err.max())}
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "parity_headline_%s.json" % np.dtype(dtype).name), "w") as f:
+            json.dump(report, f, indent=1)
+    print(json.dumps(report))
+    assert cnt[0].sum() > E                                   # the horizon is full of contacts
+    if dtype == np.float64:
+        assert int(mismatch.sum()) == 0, report["bench_schedule"]     # contact-event counts match the oracle exactly
+    else:
+        assert mismatch.mean() < 0.05, report["bench_schedule"]       # fp32: reported, not required to be exact
+
+
+def test_fast_cached_args_follow_model_edits(rb):
+    """the cached argument struct must not freeze by-value model fields.  Editing gravity MuJoCo-style
+    between two steps changes the second step; the result equals a fresh scene built with that gravity."""
+    from rigidbody_simulation_b200 import stepper, synth
+    E = 4096
+    s = synth.sphere_incline(E)
+    model, data = _scene(rb, s, E, np.float64)
+    stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=8)
+    model.opt.gravity[:] = [0.0, 1.0, -3.0]
+    stepper.step_body_plane(model, data, -1, s["dt"], None, None, 0.0, substeps=8)
+    model2, data2 = _scene(rb, s, E, np.float64)
+    stepper.step_body_plane(model2, data2, -1, s["dt"], None, None, 0.0, substeps=8)
+    model2.opt.gravity[:] = [0.0, 1.0, -3.0]
+    data2.__dict__.pop("_args_cache", None)                   # no cache at all: the struct is rebuilt from the model
+    stepper.step_body_plane(model2, data2, -1, s["dt"], None, None, 0.0, substeps=8)
+    assert torch.equal(data.state, data2.state)
+    ref = data.state.clone()
+    # a host tensor passed as restitution is re-uploaded on every call: in-place edits are seen
+    e_host = torch.full((E,), 0.5, dtype=torch.float64)
+    stepper.step_body_plane(model, data, -1, s["dt"], e_host, None, 0.0, substeps=8)
+    a = data.state.clone()
+    data.state.copy_(ref)
+    e_host.fill_(1.0)
+    stepper.step_body_plane(model, data, -1, s["dt"], e_host, None, 0.0, substeps=8)
+    assert not torch.equal(data.state, a)

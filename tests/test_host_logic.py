@@ -264,22 +264,141 @@ def test_cli_help_and_headless_flags():
             "from src.simulate import main; main(['--help'])")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
     assert r.returncode == 0
-    for flag in ("--sim", "--headless", "--steps", "--envs", "--dtype", "--substeps-per-launch", "--seed", "--gpus"):
+    for flag in ("--sim", "--headless", "--steps", "--envs", "--dtype", "--substeps-per-launch", "--seed", "--gpus", "--arith",
+                 "--config", "--bodies", "--log"):
         assert flag in r.stdout
 
 
 def test_bench_reference_arm_json_contract():
-    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with the agreed keys."""
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with the agreed keys:
+    the installed reference (baseline/_ref, kind "reference") when present, else the NumPy port (kind "port")."""
     import json
-    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--cpu-envs-per-core", "1", "--cpu-steps", "20"], cwd=ROOT, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stderr
-    line = json.loads(r.stdout.strip().splitlines()[-1])
-    assert line["impl"] == "reference" and line["metric"] == "env-substeps/s" and line["unit"] == "env-substeps/s"
-    assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
-    assert line["e2e"] == {"value": line["value"], "unit": "env-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in line["config"] and "model" not in line["config"]
+    have_ref = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "physics", "collision.py"))
+    for config in ("sphere_incline", "two_ball"):
+        r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0", "--config", config,
+                            "--cpu-seconds", "0.2"], cwd=ROOT, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        lines = r.stdout.strip().splitlines()
+        assert len(lines) == 1, r.stdout                  # exactly one JSON line on stdout
+        line = json.loads(lines[0])
+        assert line["impl"] == "reference" and line["metric"] == "env-substeps/s" and line["unit"] == "env-substeps/s"
+        assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
+        assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and line["cpu_baseline"]["cores"] >= 1
+        assert line["e2e"] == {"value": line["value"], "unit": "env-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert "workload" in line["config"] and "model" not in line["config"] and line["config"]["config"] == config
+
+
+def test_installed_reference_and_port_agree():
+    """When baseline/_ref exists (pip install --target of the unmodified reference), its step functions and the NumPy
+    port produce the same numbers on the same sample -- the port is what stands in when the copy is absent."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_baseline as cb
+    import pyport
+    from rigidbody_simulation_b200 import synth
+    if not cb.reference_installed():
+        pytest.skip("baseline/_ref not installed")
+    mj, col, ti, pu = cb._reference_modules()
+    s = synth.sphere_incline(3)
+    model = mj.MjModel.from_xml_string(pyport.single_body_xml("sphere", [0.2], plane_euler=(0.7, 0, 0)))
+    for i in range(3):
+        a, b = mj.MjData(model), mj.MjData(model)
+        for d in (a, b):
+            d.qpos[:], d.qvel[:] = s["qpos"][i], s["qvel"][i]
+        for _ in range(150):
+            col.custom_step_with_impulse_collision_friction(model, "obj", a, dt=0.009, restitution=s["restitution"][i],
+                                                            friction_coeff=s["friction"][i], contact_threshold=0.0)
+            pyport.step_scheme_a(model, "obj", b, dt=0.009, restitution=s["restitution"][i], friction_coeff=s["friction"][i],
+                                 contact_threshold=0.0)
+        assert np.array_equal(a.qpos, b.qpos) and np.array_equal(a.qvel, b.qvel)
+    assert "site-packages" not in col.__file__ and os.path.join("baseline", "_ref") in col.__file__
+
+
+def test_cli_random_configs_are_index_keyed_and_flags_reach_the_run():
+    """`--seed S` selects the randomised BASELINE config of the scenario; a shard [start, start+count) holds exactly the
+    rows of the whole batch (so `--gpus N` sees the same environments), for every scenario.  Built on a CPU device:
+    state allocation is plumbing, stepping is not available there."""
+    sys.path.insert(0, os.path.join(ROOT, "rigidbody-simulation_b200"))
+    import torch
+    from rigidbody_simulation_b200.src import simulate
+    for sim, width in (("single_sphere", 7), ("cube_incline", 7), ("ball_collision", 14), ("multi_sphere", 7 * 5)):
+        _, whole, _ = simulate.build_random(sim, 11, 0, 7, "cpu", torch.float64, bodies=5)
+        _, part, _ = simulate.build_random(sim, 4, 6, 7, "cpu", torch.float64, bodies=5)
+        _, other, _ = simulate.build_random(sim, 4, 6, 8, "cpu", torch.float64, bodies=5)
+        qw, qp, qo = (np.asarray(d.qpos.torch()) for d in (whole, part, other))
+        assert qw.shape == (11, width)
+        assert np.array_equal(qw[6:10], qp) and not np.array_equal(qp, qo)
+    # flag plumbing down to run_simulation (no CUDA here: the run itself refuses after validating its arguments)
+    seen = {}
+    orig = simulate.run_simulation
+    simulate.run_simulation = lambda *a, **k: seen.update(args=a, kw=k)
+    try:
+        simulate.main(["--sim", "single_sphere", "--envs", "1048576", "--seed", "1", "--arith", "fast", "--gpus", "1",
+                       "--substeps-per-launch", "256", "--steps", "2048"])
+    finally:
+        simulate.run_simulation = orig
+    assert seen["args"] == ("single_sphere", 2048, 1048576, "fp64", 256)
+    assert seen["kw"]["arith"] == "fast" and seen["kw"]["seed"] == 1 and seen["kw"]["config"] is None
+    if not torch.cuda.is_available():
+        with pytest.raises(SystemExit) as e:
+            simulate.run_simulation("single_sphere", envs=4, seed=1, arith="fast")
+        assert e.value.code == 1
+    with pytest.raises(SystemExit):
+        simulate.run_simulation("single_sphere", arith="sloppy")
+
+
+def test_cli_gpus_mismatch_with_launcher_is_refused():
+    code = ("import sys; sys.path.insert(0, '.');"
+            "from rigidbody_simulation_b200.src.simulate import main; main(['--sim', 'single_sphere', '--gpus', '4'])")
+    env = dict(os.environ, WORLD_SIZE="2", RANK="0", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, env=env)
+    assert r.returncode == 1 and "does not match" in r.stdout
+
+
+def test_free_function_scalar_arrays_never_alias_one_element():
+    """a one-element array for a per-item scalar (mass=np.array([2.0])) next to N batched vectors must be
+    treated as a uniform value, never as a device pointer the kernel would index with i < N; a wrong length raises."""
+    import torch
+    from rigidbody_simulation_b200.free_functions import _Batch
+    b = object.__new__(_Batch)
+    b.device, b.dtype, b.n, b.batched, b.keep, b.as_torch = torch.device("cpu"), torch.float64, None, False, [], False
+    b.vec(np.zeros((5, 3)), (3,))
+    assert b.n == 5
+    assert b.scalar(np.array([2.0])) == (None, 2.0)
+    assert b.scalar(torch.tensor([3.5])) == (None, 3.5)
+    assert b.scalar(1.25) == (None, 1.25)
+    ptr, val = b.scalar(np.arange(5.0))
+    assert ptr is not None and val == 0.0
+    with pytest.raises(ValueError):
+        b.scalar(np.arange(3.0))
+
+
+def test_tuning_options_api():
+    import rigidbody_simulation_b200 as rb
+    lib = rb._lib
+    old = lib.set_option("pf_min_substeps", 1)
+    assert old == 4 or old >= 1
+    assert lib.get_option("pf_min_substeps") == 1
+    lib.set_option("pf_min_substeps", old)
+    assert lib.get_option("pf_min_substeps") == old
+    for name in ("minb", "pf_packed", "box_minb", "box_compact", "ms_skin_percent", "ms_sorted", "probe_mode", "host_chunks"):
+        lib.get_option(name)
+    with pytest.raises(ValueError):
+        lib.get_option("no_such_knob")
+    with pytest.raises(ValueError):
+        lib.set_option("no_such_knob", 1)
+
+
+def test_numa_binding_is_best_effort():
+    """shard.bind_to_gpu_numa never raises: without a GPU (or without sysfs locality) it reports why it did nothing."""
+    from rigidbody_simulation_b200 import shard
+    before = os.sched_getaffinity(0)
+    info = shard.bind_to_gpu_numa(0)
+    assert isinstance(info, dict) and "bound" in info
+    if not info["bound"]:
+        assert os.sched_getaffinity(0) == before and "note" in info
+    else:
+        os.sched_setaffinity(0, before)
+    assert shard._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
 
 
 def test_missing_extension_fails_loudly():
