@@ -52,7 +52,8 @@ Option g_options[] = {
     {"box_minb", "RBS_BOX_MINB", {0}, 6},                    // resident CTAs per SM of the plane-frame box kernel
     {"box_compact", "RBS_BOX_COMPACT", {0}, 1},              // plane-frame box kernel: CTA-level compaction of contacts
     {"ms_skin_percent", "RBS_MS_SKIN_PERCENT", {0}, 50},     // starting skin of the adaptive partner lists
-    {"ms_sorted", "RBS_MS_SORTED", {0}, 1},                  // multi-sphere fast kernel: contact-count-sorted impulse chains
+    {"ms_kernel", "RBS_MS_KERNEL", {0}, 2},                  // multi-sphere fast policy: 2 = plane-frame kernel, 1 = first generation
+    {"ms_walk_cost", "RBS_MS_WALK_COST", {0}, 10},           // plane-frame multi-sphere kernel: cost of a list entry per substep (skin controller)
     {"probe_mode", "RBS_PROBE_MODE", {0}, 1},                // rbs_fma_probe operand mode
     {"host_chunks", "RBS_HOST_CHUNKS", {0}, 16},             // pipeline depth of rbs_run_body_plane_host
 };
@@ -87,6 +88,45 @@ struct Window {
 
 inline Window whole(const rbs_body_plane_args *a) { return {0, a->n_env, a->state, a->stride, as_stream(a->stream)}; }
 
+// Plane frame of the fused fast kernels (double on the host): rows t1, t2, n of the world->plane rotation, the
+// quaternion of that rotation (wxyz) and gravity*dt expressed in the frame.  x' is taken along n x g, so gravity has no
+// x' component and the kernels add two components per substep.
+void plane_frame(const double *n, const double *g, double dt, double *R, double *q, double *gdt_pf) {
+    double t1[3] = {0, 0, 0}, t2[3];
+    const double c[3] = {n[1] * g[2] - n[2] * g[1], n[2] * g[0] - n[0] * g[2], n[0] * g[1] - n[1] * g[0]};
+    const double clen = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    const double glen = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    if (clen > 1e-9 * glen) {
+        for (int i = 0; i < 3; ++i) t1[i] = c[i] / clen;
+    } else {                            // g parallel to n (flat ground) or g = 0: any tangent will do
+        const int ax = fabs(n[0]) < 0.9 ? 0 : 1;
+        t1[ax] = 1.0;
+        const double d = n[ax];
+        double len = 0.0;
+        for (int i = 0; i < 3; ++i) { t1[i] -= d * n[i]; len += t1[i] * t1[i]; }
+        len = sqrt(len);
+        for (int i = 0; i < 3; ++i) t1[i] /= len;
+    }
+    t2[0] = n[1] * t1[2] - n[2] * t1[1]; t2[1] = n[2] * t1[0] - n[0] * t1[2]; t2[2] = n[0] * t1[1] - n[1] * t1[0];
+    const double M[9] = {t1[0], t1[1], t1[2], t2[0], t2[1], t2[2], n[0], n[1], n[2]};
+    for (int i = 0; i < 9; ++i) R[i] = M[i];
+    const double tr = R[0] + R[4] + R[8];
+    if (tr > 0) {
+        const double s4 = 2.0 * sqrt(tr + 1.0);
+        q[0] = 0.25 * s4; q[1] = (R[7] - R[5]) / s4; q[2] = (R[2] - R[6]) / s4; q[3] = (R[3] - R[1]) / s4;
+    } else if (R[0] > R[4] && R[0] > R[8]) {
+        const double s4 = 2.0 * sqrt(1.0 + R[0] - R[4] - R[8]);
+        q[0] = (R[7] - R[5]) / s4; q[1] = 0.25 * s4; q[2] = (R[1] + R[3]) / s4; q[3] = (R[2] + R[6]) / s4;
+    } else if (R[4] > R[8]) {
+        const double s4 = 2.0 * sqrt(1.0 + R[4] - R[0] - R[8]);
+        q[0] = (R[2] - R[6]) / s4; q[1] = (R[1] + R[3]) / s4; q[2] = 0.25 * s4; q[3] = (R[5] + R[7]) / s4;
+    } else {
+        const double s4 = 2.0 * sqrt(1.0 + R[8] - R[0] - R[4]);
+        q[0] = (R[3] - R[1]) / s4; q[1] = (R[2] + R[6]) / s4; q[2] = (R[5] + R[7]) / s4; q[3] = 0.25 * s4;
+    }
+    for (int i = 0; i < 3; ++i) gdt_pf[i] = (R[3 * i] * g[0] + R[3 * i + 1] * g[1] + R[3 * i + 2] * g[2]) * dt;
+}
+
 template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_args *a, const Window &w) {
     rbs::BodyPlaneParams<T> p;
     auto at = [&](const void *base) { return base ? static_cast<const T *>(base) + w.off : nullptr; };
@@ -117,46 +157,12 @@ template <typename T> rbs::BodyPlaneParams<T> make_params(const rbs_body_plane_a
     p.hdt = (T)0.5 * p.dt;
     p.inv_hdt = (T)1 / p.hdt;
     p.inv_dt = (T)0.5 * p.inv_hdt;
-    {   // plane frame (double on the host): rows t1, t2, n; quaternion of that rotation; gravity*dt in the frame
-        const double n[3] = {a->plane_normal[0], a->plane_normal[1], a->plane_normal[2]};
-        double t1[3] = {0, 0, 0}, t2[3];
-        // x' along n x g: gravity then has no x' component and the plane-frame kernel adds two components per substep
-        const double *g = a->gravity;
-        const double c[3] = {n[1] * g[2] - n[2] * g[1], n[2] * g[0] - n[0] * g[2], n[0] * g[1] - n[1] * g[0]};
-        const double clen = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
-        const double glen = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
-        if (clen > 1e-9 * glen) {
-            for (int i = 0; i < 3; ++i) t1[i] = c[i] / clen;
-        } else {                            // g parallel to n (flat ground) or g = 0: any tangent will do
-            const int ax = fabs(n[0]) < 0.9 ? 0 : 1;
-            t1[ax] = 1.0;
-            const double d = n[ax];
-            double len = 0.0;
-            for (int i = 0; i < 3; ++i) { t1[i] -= d * n[i]; len += t1[i] * t1[i]; }
-            len = sqrt(len);
-            for (int i = 0; i < 3; ++i) t1[i] /= len;
-        }
-        t2[0] = n[1] * t1[2] - n[2] * t1[1]; t2[1] = n[2] * t1[0] - n[0] * t1[2]; t2[2] = n[0] * t1[1] - n[1] * t1[0];
-        const double R[9] = {t1[0], t1[1], t1[2], t2[0], t2[1], t2[2], n[0], n[1], n[2]};
-        double q[4];
-        const double tr = R[0] + R[4] + R[8];
-        if (tr > 0) {
-            const double s4 = 2.0 * sqrt(tr + 1.0);
-            q[0] = 0.25 * s4; q[1] = (R[7] - R[5]) / s4; q[2] = (R[2] - R[6]) / s4; q[3] = (R[3] - R[1]) / s4;
-        } else if (R[0] > R[4] && R[0] > R[8]) {
-            const double s4 = 2.0 * sqrt(1.0 + R[0] - R[4] - R[8]);
-            q[0] = (R[7] - R[5]) / s4; q[1] = 0.25 * s4; q[2] = (R[1] + R[3]) / s4; q[3] = (R[2] + R[6]) / s4;
-        } else if (R[4] > R[8]) {
-            const double s4 = 2.0 * sqrt(1.0 + R[4] - R[0] - R[8]);
-            q[0] = (R[2] - R[6]) / s4; q[1] = (R[1] + R[3]) / s4; q[2] = 0.25 * s4; q[3] = (R[5] + R[7]) / s4;
-        } else {
-            const double s4 = 2.0 * sqrt(1.0 + R[8] - R[0] - R[4]);
-            q[0] = (R[3] - R[1]) / s4; q[1] = (R[2] + R[6]) / s4; q[2] = (R[5] + R[7]) / s4; q[3] = 0.25 * s4;
-        }
+    {
+        double R[9], q[4], gpf[3];
+        plane_frame(a->plane_normal, a->gravity, a->dt, R, q, gpf);
         for (int i = 0; i < 9; ++i) p.frame[i] = (T)R[i];
         for (int i = 0; i < 4; ++i) p.frame_q[i] = (T)q[i];
-        for (int i = 0; i < 3; ++i)
-            p.gdt_pf[i] = (T)((R[3 * i] * a->gravity[0] + R[3 * i + 1] * a->gravity[1] + R[3 * i + 2] * a->gravity[2]) * a->dt);
+        for (int i = 0; i < 3; ++i) p.gdt_pf[i] = (T)gpf[i];
     }
     p.n_contacts = a->n_contacts ? a->n_contacts + w.off : nullptr;
     p.n_impulses = a->n_impulses ? a->n_impulses + w.off : nullptr;
@@ -245,6 +251,18 @@ template <typename T> void launch_box_plane_fast(const rbs_body_plane_args *a, c
         // 6.14e10 / 6.49e10 / 6.55e10 env-substeps/s bouncing, 4.39e10 / 4.63e10 / 4.69e10 sliding on the incline
         const int minb = (int)option("box_minb");
         const unsigned grid = blocks_for(w.cnt, rbs::kBlock);
+        if (option("box_compact") != 0) {
+            // CTA-level compaction of the contact path (bit-identical results; box_compact = 0 keeps one environment's
+            // whole substep in its own thread).  ~29 KB of static shared memory per CTA: ask for the large carve-out.
+            if (minb >= 6) {
+                cudaFuncSetAttribute(rbs::step_box_plane_pfc_kernel<T, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                rbs::step_box_plane_pfc_kernel<T, 6><<<grid, rbs::kBlock, 0, w.stream>>>(p);
+            } else {
+                cudaFuncSetAttribute(rbs::step_box_plane_pfc_kernel<T, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                rbs::step_box_plane_pfc_kernel<T, 5><<<grid, rbs::kBlock, 0, w.stream>>>(p);
+            }
+            return;
+        }
         switch (minb) {
             case 4: rbs::step_box_plane_pf_kernel<T, 4><<<grid, rbs::kBlock, 0, w.stream>>>(p); break;
             case 5: rbs::step_box_plane_pf_kernel<T, 5><<<grid, rbs::kBlock, 0, w.stream>>>(p); break;
@@ -364,6 +382,14 @@ template <typename T> rbs::MultiSphereParams<T> make_params(const rbs_multi_sphe
     if (a->list_skin_percent == 0 && a->substeps < 4) skin_pct = -1;
     p.skin = skin_pct > 0 ? (T)(skin_pct * 0.01) : T(0);
     p.skin_adapt = a->list_skin_percent == 0 && skin_pct > 0;
+    p.walk_cost = (int)option("ms_walk_cost");
+    {
+        double R[9], q[4], gpf[3];
+        plane_frame(a->plane_normal, a->gravity, a->dt, R, q, gpf);
+        for (int i = 0; i < 9; ++i) p.frame[i] = (T)R[i];
+        for (int i = 0; i < 4; ++i) p.frame_q[i] = (T)q[i];
+        for (int i = 0; i < 3; ++i) p.gdt_pf[i] = (T)gpf[i];
+    }
     p.n_contacts = a->n_contacts;
     p.n_impulses = a->n_impulses;
     return p;
@@ -413,6 +439,29 @@ template <typename T> int launch_multi_sphere(const rbs_multi_sphere_args *a) {
         }                                                                                                       \
         KERNEL<<<grid, threads, smem, st>>>(p);                                                                 \
     } while (0)
+    if (a->arith == RBS_ARITH_FAST && option("ms_kernel") >= 2) {
+        // plane-frame kernel (SoA centres in both precisions, two-phase list walk); MU0: frictionless spheres
+        const size_t smem_pf = rbs::PairListsSoA<T>::smem_bytes(epb, B, threads);
+        const size_t smem_old = smem;
+        (void)smem_old;
+#define RBS_MS_LAUNCH_PF(KERNEL)                                                                                \
+    do {                                                                                                        \
+        if (smem_pf > 48 * 1024) {                                                                              \
+            const cudaError_t e__ = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pf); \
+            if (e__ != cudaSuccess) {                                                                           \
+                cudaGetLastError();                                                                             \
+                return fail(RBS_ECUDA, "rbs_step_multi_sphere: %zu bytes of shared memory: %s", smem_pf, cudaGetErrorString(e__)); \
+            }                                                                                                   \
+        }                                                                                                       \
+        KERNEL<<<grid, threads, smem_pf, st>>>(p);                                                              \
+    } while (0)
+        const bool mu0 = a->friction == 0.0;
+        if (threads <= 256) { if (mu0) RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 256, true>)); else RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 256, false>)); }
+        else if (threads <= 512) { if (mu0) RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 512, true>)); else RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 512, false>)); }
+        else { if (mu0) RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 1024, true>)); else RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 1024, false>)); }
+#undef RBS_MS_LAUNCH_PF
+        return RBS_OK;
+    }
     if (a->arith == RBS_ARITH_FAST) {
         if (threads <= 256) RBS_MS_LAUNCH((rbs::step_multi_sphere_fast_kernel<T, 256>));
         else if (threads <= 512) RBS_MS_LAUNCH((rbs::step_multi_sphere_fast_kernel<T, 512>));

@@ -25,15 +25,15 @@ def single_body_xml(geom, size, plane_euler=(0.0, 0.0, 0.0), body_pos=(0.0, 0.0,
             f'</worldbody></mujoco>')
 
 
-def multi_sphere_xml(n_body, radius=0.1, timestep=0.01, gravity=(0.0, 0.0, -9.8), density=50.0):
-    """Same shape as models/multi_sphere.xml, scaled to ``n_body`` spheres ball1..ballN."""
+def multi_sphere_xml(n_body, radius=0.1, timestep=0.01, gravity=(0.0, 0.0, -9.8), density=50.0, plane_euler=(0.0, 0.0, 0.0)):
+    """Same shape as models/multi_sphere.xml, scaled to ``n_body`` spheres ball1..ballN (``plane_euler`` tilts the ground)."""
     fmt = lambda v: " ".join(repr(float(x)) for x in v)
     balls = "".join(f'<body name="ball{i + 1}" pos="0 0 {1 + i}"><joint name="ball_joint{i + 1}" type="free"/>'
                     f'<geom name="ball_geom{i + 1}" type="sphere" size="{float(radius)!r}" density="{float(density)!r}"/>'
                     f'</body>' for i in range(n_body))
     return (f'<mujoco><compiler angle="radian" inertiafromgeom="true"/>'
             f'<option gravity="{fmt(gravity)}" timestep="{float(timestep)!r}"/><worldbody>'
-            f'<geom name="ground" type="plane" size="5 5 0.1"/>{balls}</worldbody></mujoco>')
+            f'<geom name="ground" type="plane" size="5 5 0.1" euler="{fmt(plane_euler)}"/>{balls}</worldbody></mujoco>')
 
 
 def sphere_on_incline(nenv, theta=0.7, device=None, dtype=torch.float64):

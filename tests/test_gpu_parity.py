@@ -437,25 +437,27 @@ def test_multi_sphere_golden(rb, golden):
         assert calls[0].tolist() == case["calls"] and imps[0].tolist() == case["impulses"]
 
 
-@pytest.mark.parametrize("arith", ["strict", "fast"])
+@pytest.mark.parametrize("arith,mu", [("strict", 0.3), ("fast", 0.3), ("fast", 0.0), ("strict", 0.0)])
 @pytest.mark.parametrize("dtype,tol", [(np.float64, F64_STEP), (np.float32, F32_STEP)])
 @pytest.mark.parametrize("B", [64, 27, 5])
-def test_multi_sphere_vs_oracle(rb, dtype, tol, B, arith):
+def test_multi_sphere_vs_oracle(rb, dtype, tol, B, arith, mu):
+    """mu = 0.3 exercises the friction path; mu = 0.0 is the shipped multi_sphere config (sim_overrides.py:22-27), which
+    the fast policy runs through its frictionless instantiation (normal impulses only, closed-form orientation)."""
     from rigidbody_simulation_b200 import stepper, synth
     from rigidbody_simulation_b200.src.simulation import multi_sphere_bounce as ms
     E = 1500 if B == 64 else 4000
-    s = synth.multi_sphere(E, n_body=B, friction=0.3)
+    s = synth.multi_sphere(E, n_body=B, friction=mu)
     model, data = ms.build(E, n_body=B, dtype=tdt(dtype))
     data.set_state(s["qpos"], s["qvel"])
     qp = s["qpos"].astype(dtype).reshape(E, B, 7).copy()
     qv = s["qvel"].astype(dtype).reshape(E, B, 6).copy()
     cnt = (np.zeros((E, B), np.uint32), np.zeros((E, B), np.uint32))
     okw = dict(mass=model.body_mass[1], inertia=model.body_inertia[1], radius=0.1, plane_pos=[0, 0, 0], plane_normal=[0, 0, 1],
-               gravity=G, dt=0.01, restitution=1.0, friction=0.3, counters=cnt)
+               gravity=G, dt=0.01, restitution=1.0, friction=mu, counters=cnt)
     done = 0
     for upto in (1, 10, 60):
         co.step_multi_sphere(qp, qv, upto - done, **okw)
-        stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.3, substeps=upto - done, arith=arith)
+        stepper.step_multi_sphere(model, data, 0.01, 1.0, mu, substeps=upto - done, arith=arith)
         done = upto
         gq, gv = state_of(data)
         # components that cancel to ~0 carry the absolute rounding error of O(1) intermediates; in fp32 under the
@@ -475,6 +477,48 @@ def test_multi_sphere_vs_oracle(rb, dtype, tol, B, arith):
         else:
             assert mismatch.mean() <= 1e-3, mismatch.mean() # re-associated arithmetic on chaotic piles: a vanishing fraction
     assert cnt[0].sum() > E * B                              # contacts are exercised
+
+
+def test_multi_sphere_tilted_ground_and_mixed_radii_vs_oracle(rb):
+    """The plane-frame multi-sphere kernels on a tilted ground (so the frame rotation is not the identity) with
+    per-body radii, with and without friction, against the oracle: one step within the bar, a short horizon within
+    what collisions amplify, exact event counts after 10 steps; the strict policy stays bit for bit."""
+    from rigidbody_simulation_b200 import scenes, stepper, synth
+    import rigidbody_simulation_b200.mj as mj
+    E, B = 800, 40
+    s = synth.multi_sphere(E, n_body=B, friction=0.0)
+    theta = 0.35
+    normal = [0.0, -np.sin(theta), np.cos(theta)]
+    radii = 0.08 + 0.04 * (np.arange(E * B) % B) / B
+    for mu in (0.0, 0.4):
+        for arith in ("fast", "strict"):
+            model = mj.MjModel.from_xml_string(scenes.multi_sphere_xml(B, plane_euler=(theta, 0, 0)), nenv=E)
+            data = mj.MjData(model, layout="body")
+            m, I = float(model.body_mass[1]), [float(x) for x in model.body_inertia[1]]
+            r = torch.tensor(radii, dtype=torch.float64, device="cuda")
+            model.set_per_env(radius=r, mass=torch.full_like(r, m), inertia=torch.full((3, E * B), I[0], dtype=torch.float64, device="cuda"))
+            data.set_state(s["qpos"], s["qvel"])
+            qp, qv = s["qpos"].reshape(E, B, 7).copy(), s["qvel"].reshape(E, B, 6).copy()
+            cnt = (np.zeros((E, B), np.uint32), np.zeros((E, B), np.uint32))
+            okw = dict(mass=m, inertia=I, radius=radii.reshape(E, B), plane_pos=[0, 0, 0], plane_normal=normal, gravity=G, dt=0.01,
+                       restitution=1.0, friction=mu, counters=cnt)
+            done = 0
+            for upto in (1, 10, 40):
+                co.step_multi_sphere(qp, qv, upto - done, **okw)
+                stepper.step_multi_sphere(model, data, 0.01, 1.0, mu, substeps=upto - done, arith=arith)
+                done = upto
+                gq, gv = state_of(data)
+                err = max(comp_rel_err(gq.ravel(), qp.ravel(), 1e-3), comp_rel_err(gv.ravel(), qv.ravel(), 1e-3))
+                if arith == "strict":
+                    assert err == 0.0, (mu, upto, err)
+                elif upto == 1:
+                    assert err <= F64_STEP, (mu, upto, err)
+                elif upto == 10:
+                    assert err <= 1e-9, (mu, upto, err)
+                    calls, imps = data.counters()
+                    assert (calls == cnt[0]).all() and (imps == cnt[1]).all(), mu
+            assert cnt[0].sum() > E * B // 2 and cnt[1].sum() > 0
+            assert np.isfinite(gq).all() and np.abs(np.sqrt((gq.reshape(E, B, 7)[:, :, 3:] ** 2).sum(-1)) - 1).max() < 1e-12
 
 
 # ------------------------------------------------------------------------------------ properties at full size
