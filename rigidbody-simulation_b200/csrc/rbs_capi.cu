@@ -50,10 +50,11 @@ Option g_options[] = {
     {"pf_min_substeps", "RBS_PF_MIN_SUBSTEPS", {0}, 4},      // shortest launch that takes the plane-frame kernels
     {"pf_packed", "RBS_PF_PACKED", {0}, 1},                  // float sphere stepper: packed fp32x2 kernel (1) or scalar (0)
     {"box_minb", "RBS_BOX_MINB", {0}, 6},                    // resident CTAs per SM of the plane-frame box kernel
-    {"box_compact", "RBS_BOX_COMPACT", {0}, 1},              // plane-frame box kernel: CTA-level compaction of contacts
+    {"box_compact", "RBS_BOX_COMPACT", {0}, 0},              // plane-frame box kernel: CTA-level compaction of contacts (measured slower: off)
+    {"tb_minb", "RBS_TB_MINB", {0}, 0},                      // resident CTAs per SM of the two-ball fast kernel (5, 6 or 8; 0 = 6 in double, 8 in float)
     {"ms_skin_percent", "RBS_MS_SKIN_PERCENT", {0}, 50},     // starting skin of the adaptive partner lists
     {"ms_kernel", "RBS_MS_KERNEL", {0}, 2},                  // multi-sphere fast policy: 2 = plane-frame kernel, 1 = first generation
-    {"ms_walk_cost", "RBS_MS_WALK_COST", {0}, 10},           // plane-frame multi-sphere kernel: cost of a list entry per substep (skin controller)
+    {"ms_walk_cost", "RBS_MS_WALK_COST", {0}, 16},           // plane-frame multi-sphere kernel: cost of a list entry per substep (skin controller)
     {"probe_mode", "RBS_PROBE_MODE", {0}, 1},                // rbs_fma_probe operand mode
     {"host_chunks", "RBS_HOST_CHUNKS", {0}, 16},             // pipeline depth of rbs_run_body_plane_host
 };
@@ -80,8 +81,8 @@ inline size_t elem_size(int dtype) { return dtype == RBS_F64 ? sizeof(double) : 
 // A launch may cover a window [off, off+cnt) of the environments described by `a` (the host-buffer driver
 // pipelines chunks); per-env parameter arrays keep their full-size row stride.
 struct Window {
-    long off, cnt;
-    void *state;
+    long off, cnt;             // environments [off, off + cnt) of the batch described by the argument struct
+    void *state;               // SoA state of the window
     long stride;
     cudaStream_t stream;
 };
@@ -316,14 +317,18 @@ int validate_body_plane(const rbs_body_plane_args *a, bool need_state) {
     return RBS_OK;
 }
 
-template <typename T> rbs::TwoBallParams<T> make_params(const rbs_two_ball_args *a) {
+inline Window whole(const rbs_two_ball_args *a) { return {0, a->n_env, a->state, a->stride, as_stream(a->stream)}; }
+inline Window whole(const rbs_multi_sphere_args *a) { return {0, a->n_env, a->state, a->stride, as_stream(a->stream)}; }
+
+template <typename T> rbs::TwoBallParams<T> make_params(const rbs_two_ball_args *a, const Window &w) {
     rbs::TwoBallParams<T> p;
-    p.n_env = a->n_env;
-    p.stride = a->stride;
+    p.n_env = w.cnt;
+    p.stride = w.stride;
+    p.pstride = a->n_env;                        // mass is [2][n_env] of the whole batch
     p.substeps = a->substeps;
-    p.state = static_cast<T *>(a->state);
-    p.mass = static_cast<const T *>(a->mass);
-    p.radius = static_cast<const T *>(a->radius);
+    p.state = static_cast<T *>(w.state);
+    p.mass = a->mass ? static_cast<const T *>(a->mass) + w.off : nullptr;
+    p.radius = a->radius ? static_cast<const T *>(a->radius) + w.off : nullptr;
     p.mass_u[0] = (T)a->mass_u[0];
     p.mass_u[1] = (T)a->mass_u[1];
     p.radius_u = (T)a->radius_u;
@@ -333,8 +338,8 @@ template <typename T> rbs::TwoBallParams<T> make_params(const rbs_two_ball_args 
     p.fric = (T)a->friction;
     for (int i = 0; i < 3; ++i) p.gdt[i] = p.g[i] * p.dt;
     p.neg1pe = -((T)1 + p.rest);
-    p.n_ground = a->n_ground_hits;
-    p.n_pair = a->n_pair_hits;
+    p.n_ground = a->n_ground_hits ? a->n_ground_hits + w.off : nullptr;
+    p.n_pair = a->n_pair_hits ? a->n_pair_hits + w.off : nullptr;
     return p;
 }
 
@@ -351,17 +356,19 @@ int validate_two_ball(const rbs_two_ball_args *a, bool need_state) {
     return RBS_OK;
 }
 
-template <typename T> rbs::MultiSphereParams<T> make_params(const rbs_multi_sphere_args *a, int env_per_block) {
+template <typename T> rbs::MultiSphereParams<T> make_params(const rbs_multi_sphere_args *a, const Window &w, int env_per_block) {
     rbs::MultiSphereParams<T> p;
-    p.n_env = a->n_env;
-    p.stride = a->stride;
+    const long boff = w.off * a->n_body;         // per-body arrays are indexed env * n_body + body
+    p.n_env = w.cnt;
+    p.stride = w.stride;
+    p.pstride = a->n_env * a->n_body;            // inertia is [3][n_env * n_body] of the whole batch
     p.substeps = a->substeps;
     p.n_body = a->n_body;
     p.env_per_block = env_per_block;
-    p.state = static_cast<T *>(a->state);
-    p.mass = static_cast<const T *>(a->mass);
-    p.inertia = static_cast<const T *>(a->inertia);
-    p.radius = static_cast<const T *>(a->radius);
+    p.state = static_cast<T *>(w.state);
+    p.mass = a->mass ? static_cast<const T *>(a->mass) + boff : nullptr;
+    p.inertia = a->inertia ? static_cast<const T *>(a->inertia) + boff : nullptr;
+    p.radius = a->radius ? static_cast<const T *>(a->radius) + boff : nullptr;
     p.mass_u = (T)a->mass_u;
     p.radius_u = (T)a->radius_u;
     for (int i = 0; i < 3; ++i) {
@@ -390,8 +397,8 @@ template <typename T> rbs::MultiSphereParams<T> make_params(const rbs_multi_sphe
         for (int i = 0; i < 4; ++i) p.frame_q[i] = (T)q[i];
         for (int i = 0; i < 3; ++i) p.gdt_pf[i] = (T)gpf[i];
     }
-    p.n_contacts = a->n_contacts;
-    p.n_impulses = a->n_impulses;
+    p.n_contacts = a->n_contacts ? a->n_contacts + boff : nullptr;
+    p.n_impulses = a->n_impulses ? a->n_impulses + boff : nullptr;
     return p;
 }
 
@@ -414,17 +421,23 @@ int validate_multi_sphere(const rbs_multi_sphere_args *a, bool need_state) {
     return RBS_OK;
 }
 
-template <typename T> int launch_multi_sphere(const rbs_multi_sphere_args *a) {
+inline void multi_sphere_shape(int B, int *threads, int *epb) {
+    int t = ((B + 31) / 32) * 32;
+    if (t < 128) t = 128;
+    *threads = t;
+    *epb = t / B;
+}
+
+template <typename T> int launch_multi_sphere(const rbs_multi_sphere_args *a, const Window &w) {
     const int B = a->n_body;
-    int threads = ((B + 31) / 32) * 32;
-    if (threads < 128) threads = 128;
-    const int epb = threads / B;
-    const rbs::MultiSphereParams<T> p = make_params<T>(a, epb);
-    const unsigned grid = (unsigned)((a->n_env + epb - 1) / epb);
+    int threads, epb;
+    multi_sphere_shape(B, &threads, &epb);
+    const rbs::MultiSphereParams<T> p = make_params<T>(a, w, epb);
+    const unsigned grid = (unsigned)((w.cnt + epb - 1) / epb);
     // two buffers of centres + fp32 relative copies + partner lists (ceil(B/64) words per thread, word-major)
     const size_t smem = 2 * (size_t)epb * B * 4 * sizeof(T) + (size_t)epb * B * sizeof(float4) +
                         (size_t)((B + 63) / 64) * threads * sizeof(unsigned long long);
-    cudaStream_t st = as_stream(a->stream);
+    cudaStream_t st = w.stream;
     const bool iso = a->inertia_mode == RBS_INERTIA_ISOTROPIC;
     // above 48 KB (B > ~450) the dynamic shared memory needs the opt-in attribute.  It is a property of the function on
     // the CURRENT device, so it is set on every such launch (cheap) rather than remembered per process.
@@ -482,6 +495,40 @@ template <typename T> int launch_multi_sphere(const rbs_multi_sphere_args *a) {
     return RBS_OK;
 }
 
+int launch_two_ball_any(const rbs_two_ball_args *a, const Window &w) {
+    const unsigned grid = blocks_for(w.cnt, rbs::kBlock);
+    cudaStream_t st = w.stream;
+    if (a->arith == RBS_ARITH_FAST) {
+        // gravity along z only (every shipped model): the additions of +0.0 to the horizontal velocities are not issued
+        const bool gz = a->gravity[0] == 0.0 && a->gravity[1] == 0.0;
+        // resident CTAs per SM (register cap 64 / 80 / 96); spins and per-ball constants live in shared memory
+        int minb = (int)option("tb_minb");
+        if (minb == 0) minb = a->dtype == RBS_F64 ? 6 : 8;     // measured on B200, 1M envs: profiles/r2_ab_two_ball.jsonl
+#define RBS_TB(T, GZ, MINB)                                                                                              \
+    do {                                                                                                                 \
+        cudaFuncSetAttribute(rbs::step_two_ball_fast_kernel<T, GZ, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                             cudaSharedmemCarveoutMaxShared);                                                            \
+        rbs::step_two_ball_fast_kernel<T, GZ, MINB><<<grid, rbs::kBlock, 0, st>>>(make_params<T>(a, w));                    \
+    } while (0)
+#define RBS_TB_MINB(T, GZ) do { if (minb >= 8) RBS_TB(T, GZ, 8); else if (minb >= 6) RBS_TB(T, GZ, 6); else RBS_TB(T, GZ, 5); } while (0)
+        if (a->dtype == RBS_F64) { if (gz) RBS_TB_MINB(double, true); else RBS_TB_MINB(double, false); }
+        else { if (gz) RBS_TB_MINB(float, true); else RBS_TB_MINB(float, false); }
+#undef RBS_TB_MINB
+#undef RBS_TB
+    } else if (a->dtype == RBS_F64) {
+        rbs::step_two_ball_kernel<double><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a, w));
+    } else {
+        rbs::step_two_ball_kernel<float><<<grid, rbs::kBlock, 0, st>>>(make_params<float>(a, w));
+    }
+    return check_launch("rbs_step_two_ball");
+}
+
+int launch_multi_sphere_any(const rbs_multi_sphere_args *a, const Window &w) {
+    const int rc = a->dtype == RBS_F64 ? launch_multi_sphere<double>(a, w) : launch_multi_sphere<float>(a, w);
+    if (rc) return rc;
+    return check_launch("rbs_step_multi_sphere");
+}
+
 // cached device workspace of the host-buffer drivers -------------------------------------------
 std::mutex g_ws_mutex;
 void *g_ws = nullptr;
@@ -505,7 +552,7 @@ int workspace(size_t bytes, void **out) {
 }
 
 // streams / events of the pipelined host driver (created once per process) ---------------------------------
-constexpr int kMaxChunks = 8;
+constexpr int kMaxChunks = 32;
 struct Pipe {
     bool ready = false;
     int device = -1;
@@ -546,50 +593,94 @@ int pipe_init() {
     return RBS_OK;
 }
 
+int pipe_init_locked() {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    return pipe_init();
+}
+
 #define RBS_CUDA(call)                                                                   \
     do {                                                                                 \
         cudaError_t err__ = (call);                                                      \
         if (err__ != cudaSuccess) return fail(RBS_ECUDA, #call ": %s", cudaGetErrorString(err__)); \
     } while (0)
 
-// shared skeleton of the three host drivers: H2D, pack, step loop, unpack, D2H, sync
-template <typename Args, typename StepFn>
-int run_host(const Args *a, int n_body, int body_fastest, void *qpos_host, void *qvel_host, long total_steps,
-             StepFn step) {
+// The host-buffer drivers, pipelined over chunks of environments: while chunk c is being stepped, chunk c+1 is on its
+// way in over PCIe and chunk c-1 on its way out (three internal streams; the caller's stream is joined at the end).
+// Chunks are whole numbers of `quantum` environments (one wave of resident CTAs of the stepping kernel), so that no
+// chunk ends in a ragged partial wave.  Only the first copy-in and the last copy-out are exposed, so the first and the
+// last chunk are one quantum; the ones in between share the rest (at most `host_chunks` chunks, option of that name).
+// `launch(local_args, window)` enqueues one launch of local_args->substeps substeps on the window's stream.
+template <typename Args, typename LaunchFn>
+int run_host_pipelined(const Args *a, int n_body, int body_fastest, long quantum, void *qpos_host, void *qvel_host,
+                       long total_steps, LaunchFn launch) {
     if (total_steps < 0) return fail(RBS_EINVAL, "total_steps %ld < 0", total_steps);
     if (a->n_env == 0) return RBS_OK;
     if (!qpos_host || !qvel_host) return fail(RBS_EINVAL, "null host buffer");
     std::lock_guard<std::mutex> lock(g_ws_mutex);
-    int rc0 = pipe_init();
-    if (rc0) return rc0;
+    int rc = pipe_init();
+    if (rc) return rc;
     const size_t es = elem_size(a->dtype);
-    const size_t nb = (size_t)a->n_env * n_body;
-    const size_t qpos_bytes = nb * 7 * es, qvel_bytes = nb * 6 * es, state_bytes = nb * 13 * es;
+    const long E = a->n_env;
+    const size_t per_env = (size_t)n_body * es;              // bytes of one scalar row entry group per environment
     void *base = nullptr;
-    int rc = workspace(qpos_bytes + qvel_bytes + state_bytes, &base);
+    rc = workspace((size_t)E * 26 * per_env, &base);
     if (rc) return rc;
-    char *qpos_d = static_cast<char *>(base), *qvel_d = qpos_d + qpos_bytes, *state_d = qvel_d + qvel_bytes;
-    cudaStream_t stream = as_stream(a->stream);
-    RBS_CUDA(cudaMemcpyAsync(qpos_d, qpos_host, qpos_bytes, cudaMemcpyHostToDevice, stream));
-    RBS_CUDA(cudaMemcpyAsync(qvel_d, qvel_host, qvel_bytes, cudaMemcpyHostToDevice, stream));
-    const long stride = body_fastest ? (long)nb : a->n_env;
-    rc = rbs_pack_state(a->dtype, a->n_env, n_body, body_fastest, qpos_d, qvel_d, state_d, stride, a->stream);
-    if (rc) return rc;
-    Args local = *a;
-    local.state = state_d;
-    local.stride = stride;
-    for (long done = 0; done < total_steps;) {
-        const long k = total_steps - done < a->substeps ? total_steps - done : a->substeps;
-        local.substeps = (int)k;
-        rc = step(&local);
-        if (rc) return rc;
-        done += k;
+    char *qpos_d = static_cast<char *>(base), *qvel_d = qpos_d + (size_t)E * 7 * per_env, *state_d = qvel_d + (size_t)E * 6 * per_env;
+    long max_chunks = option("host_chunks");
+    if (max_chunks < 3) max_chunks = 3;
+    if (max_chunks > kMaxChunks) max_chunks = kMaxChunks;
+    if (quantum < 1) quantum = 1;
+    long offs[kMaxChunks + 1];
+    int n_chunks = 0;
+    offs[0] = 0;
+    if (E <= 3 * quantum) {
+        offs[++n_chunks] = E;
+    } else {
+        offs[++n_chunks] = quantum;
+        const long middle = E - 2 * quantum;
+        const long n_mid = max_chunks - 2;
+        long per = (middle + n_mid - 1) / n_mid;
+        per = ((per + quantum - 1) / quantum) * quantum;
+        for (long done = 0; done < middle; done += per) offs[n_chunks + 1] = offs[n_chunks] + (middle - done < per ? middle - done : per), ++n_chunks;
+        offs[n_chunks + 1] = E, ++n_chunks;
     }
-    rc = rbs_unpack_state(a->dtype, a->n_env, n_body, body_fastest, state_d, stride, qpos_d, qvel_d, a->stream);
-    if (rc) return rc;
-    RBS_CUDA(cudaMemcpyAsync(qpos_host, qpos_d, qpos_bytes, cudaMemcpyDeviceToHost, stream));
-    RBS_CUDA(cudaMemcpyAsync(qvel_host, qvel_d, qvel_bytes, cudaMemcpyDeviceToHost, stream));
-    RBS_CUDA(cudaStreamSynchronize(stream));
+    cudaStream_t user = as_stream(a->stream);
+    RBS_CUDA(cudaEventRecord(g_pipe.start, user));
+    RBS_CUDA(cudaStreamWaitEvent(g_pipe.in, g_pipe.start, 0));
+    for (int c = 0; c < n_chunks; ++c) {
+        const size_t off = (size_t)offs[c], cnt = (size_t)(offs[c + 1] - offs[c]);
+        RBS_CUDA(cudaMemcpyAsync(qpos_d + off * 7 * per_env, (char *)qpos_host + off * 7 * per_env, cnt * 7 * per_env, cudaMemcpyHostToDevice, g_pipe.in));
+        RBS_CUDA(cudaMemcpyAsync(qvel_d + off * 6 * per_env, (char *)qvel_host + off * 6 * per_env, cnt * 6 * per_env, cudaMemcpyHostToDevice, g_pipe.in));
+        RBS_CUDA(cudaEventRecord(g_pipe.arrived[c], g_pipe.in));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        const long off = offs[c], cnt = offs[c + 1] - offs[c];
+        cudaStream_t cs = g_pipe.compute[c & 1];
+        char *state_c = state_d + (size_t)off * 13 * per_env;
+        char *qp_c = qpos_d + (size_t)off * 7 * per_env, *qv_c = qvel_d + (size_t)off * 6 * per_env;
+        const long stride_c = body_fastest ? cnt * n_body : cnt;
+        RBS_CUDA(cudaStreamWaitEvent(cs, g_pipe.arrived[c], 0));
+        rc = rbs_pack_state(a->dtype, cnt, n_body, body_fastest, qp_c, qv_c, state_c, stride_c, cs);
+        if (rc) return rc;
+        Args local = *a;
+        const Window w{off, cnt, state_c, stride_c, cs};
+        for (long done = 0; done < total_steps;) {
+            const long k = total_steps - done < a->substeps ? total_steps - done : a->substeps;
+            local.substeps = (int)k;
+            rc = launch(&local, w);
+            if (rc) return rc;
+            done += k;
+        }
+        rc = rbs_unpack_state(a->dtype, cnt, n_body, body_fastest, state_c, stride_c, qp_c, qv_c, cs);
+        if (rc) return rc;
+        RBS_CUDA(cudaEventRecord(g_pipe.stepped[c], cs));
+        RBS_CUDA(cudaStreamWaitEvent(g_pipe.out, g_pipe.stepped[c], 0));
+        RBS_CUDA(cudaMemcpyAsync((char *)qpos_host + (size_t)off * 7 * per_env, qp_c, (size_t)cnt * 7 * per_env, cudaMemcpyDeviceToHost, g_pipe.out));
+        RBS_CUDA(cudaMemcpyAsync((char *)qvel_host + (size_t)off * 6 * per_env, qv_c, (size_t)cnt * 6 * per_env, cudaMemcpyDeviceToHost, g_pipe.out));
+    }
+    RBS_CUDA(cudaEventRecord(g_pipe.finished, g_pipe.out));
+    RBS_CUDA(cudaStreamWaitEvent(user, g_pipe.finished, 0));
+    RBS_CUDA(cudaStreamSynchronize(user));
     return RBS_OK;
 }
 
@@ -738,33 +829,14 @@ int rbs_step_two_ball(const rbs_two_ball_args *a) {
     int rc = validate_two_ball(a, true);
     if (rc) return rc;
     if (a->n_env == 0) return RBS_OK;
-    const unsigned grid = blocks_for(a->n_env, rbs::kBlock);
-    cudaStream_t st = as_stream(a->stream);
-    if (a->arith == RBS_ARITH_FAST) {
-        // gravity along z only (every shipped model): the additions of +0.0 to the horizontal velocities are not issued
-        const bool gz = a->gravity[0] == 0.0 && a->gravity[1] == 0.0;
-        if (a->dtype == RBS_F64) {
-            if (gz) rbs::step_two_ball_fast_kernel<double, true><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a));
-            else rbs::step_two_ball_fast_kernel<double, false><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a));
-        } else {
-            if (gz) rbs::step_two_ball_fast_kernel<float, true><<<grid, rbs::kBlock, 0, st>>>(make_params<float>(a));
-            else rbs::step_two_ball_fast_kernel<float, false><<<grid, rbs::kBlock, 0, st>>>(make_params<float>(a));
-        }
-    } else if (a->dtype == RBS_F64) {
-        rbs::step_two_ball_kernel<double><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a));
-    } else {
-        rbs::step_two_ball_kernel<float><<<grid, rbs::kBlock, 0, st>>>(make_params<float>(a));
-    }
-    return check_launch("rbs_step_two_ball");
+    return launch_two_ball_any(a, whole(a));
 }
 
 int rbs_step_multi_sphere(const rbs_multi_sphere_args *a) {
     int rc = validate_multi_sphere(a, true);
     if (rc) return rc;
     if (a->n_env == 0) return RBS_OK;
-    rc = a->dtype == RBS_F64 ? launch_multi_sphere<double>(a) : launch_multi_sphere<float>(a);
-    if (rc) return rc;
-    return check_launch("rbs_step_multi_sphere");
+    return launch_multi_sphere_any(a, whole(a));
 }
 
 int rbs_pack_state(int dtype, long n_env, int n_body, int body_fastest, const void *qpos, const void *qvel,
@@ -814,89 +886,33 @@ int rbs_reset_envs(int dtype, long n_env, int n_body, int body_fastest, void *st
     return check_launch("rbs_reset_envs");
 }
 
-// Pipelined over chunks of environments: while chunk c is being stepped, chunk c+1 is on its way in over PCIe
-// and chunk c-1 on its way out (three internal streams; the caller's stream is joined at the end).
 int rbs_run_body_plane_host(const rbs_body_plane_args *a, void *qpos_host, void *qvel_host, long total_steps) {
     int rc = validate_body_plane(a, false);
     if (rc) return rc;
-    if (total_steps < 0) return fail(RBS_EINVAL, "total_steps %ld < 0", total_steps);
     if (a->trajectory) return fail(RBS_EINVAL, "rbs_run_body_plane_host: trajectory sampling needs device-resident stepping");
-    if (a->n_env == 0) return RBS_OK;
-    if (!qpos_host || !qvel_host) return fail(RBS_EINVAL, "null host buffer");
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    const size_t es = elem_size(a->dtype);
-    const long E = a->n_env;
-    rc = pipe_init();
+    rc = pipe_init_locked();
     if (rc) return rc;
-    void *base = nullptr;
-    rc = workspace((size_t)E * 26 * es, &base);
-    if (rc) return rc;
-    char *qpos_d = static_cast<char *>(base), *qvel_d = qpos_d + (size_t)E * 7 * es, *state_d = qvel_d + (size_t)E * 6 * es;
-    // Chunks are whole numbers of CTA waves (no chunk ends in a ragged partial wave).  Only the first copy-in and the
-    // last copy-out are exposed, so the first and the last chunk are one wave quantum; the ones in between share the rest.
-    const long quantum = (long)g_pipe.sm_count * 4 * rbs::kBlock;
-    long offs[kMaxChunks + 1];
-    int n_chunks = 0;
-    offs[0] = 0;
-    if (E <= 3 * quantum) {
-        offs[++n_chunks] = E;
-    } else {
-        offs[++n_chunks] = quantum;
-        const long middle = E - 2 * quantum;
-        const int n_mid = kMaxChunks - 2;
-        long per = (middle + n_mid - 1) / n_mid;
-        per = ((per + quantum - 1) / quantum) * quantum;
-        for (long done = 0; done < middle; done += per) offs[n_chunks + 1] = offs[n_chunks] + (middle - done < per ? middle - done : per), ++n_chunks;
-        offs[n_chunks + 1] = E, ++n_chunks;
-    }
-    cudaStream_t user = as_stream(a->stream);
-    RBS_CUDA(cudaEventRecord(g_pipe.start, user));
-    RBS_CUDA(cudaStreamWaitEvent(g_pipe.in, g_pipe.start, 0));
-    for (int c = 0; c < n_chunks; ++c) {
-        const long off = offs[c], cnt = offs[c + 1] - offs[c];
-        RBS_CUDA(cudaMemcpyAsync(qpos_d + off * 7 * es, (char *)qpos_host + off * 7 * es, cnt * 7 * es, cudaMemcpyHostToDevice, g_pipe.in));
-        RBS_CUDA(cudaMemcpyAsync(qvel_d + off * 6 * es, (char *)qvel_host + off * 6 * es, cnt * 6 * es, cudaMemcpyHostToDevice, g_pipe.in));
-        RBS_CUDA(cudaEventRecord(g_pipe.arrived[c], g_pipe.in));
-    }
-    for (int c = 0; c < n_chunks; ++c) {
-        const long off = offs[c], cnt = offs[c + 1] - offs[c];
-        cudaStream_t cs = g_pipe.compute[c & 1];
-        char *state_c = state_d + off * 13 * es;
-        RBS_CUDA(cudaStreamWaitEvent(cs, g_pipe.arrived[c], 0));
-        rc = rbs_pack_state(a->dtype, cnt, 1, 0, qpos_d + off * 7 * es, qvel_d + off * 6 * es, state_c, cnt, cs);
-        if (rc) return rc;
-        rbs_body_plane_args local = *a;
-        const Window w{off, cnt, state_c, cnt, cs};
-        for (long done = 0; done < total_steps;) {
-            const long k = total_steps - done < a->substeps ? total_steps - done : a->substeps;
-            local.substeps = (int)k;
-            rc = launch_body_plane_any(&local, w);
-            if (rc) return rc;
-            done += k;
-        }
-        rc = rbs_unpack_state(a->dtype, cnt, 1, 0, state_c, cnt, qpos_d + off * 7 * es, qvel_d + off * 6 * es, cs);
-        if (rc) return rc;
-        RBS_CUDA(cudaEventRecord(g_pipe.stepped[c], cs));
-        RBS_CUDA(cudaStreamWaitEvent(g_pipe.out, g_pipe.stepped[c], 0));
-        RBS_CUDA(cudaMemcpyAsync((char *)qpos_host + off * 7 * es, qpos_d + off * 7 * es, cnt * 7 * es, cudaMemcpyDeviceToHost, g_pipe.out));
-        RBS_CUDA(cudaMemcpyAsync((char *)qvel_host + off * 6 * es, qvel_d + off * 6 * es, cnt * 6 * es, cudaMemcpyDeviceToHost, g_pipe.out));
-    }
-    RBS_CUDA(cudaEventRecord(g_pipe.finished, g_pipe.out));
-    RBS_CUDA(cudaStreamWaitEvent(user, g_pipe.finished, 0));
-    RBS_CUDA(cudaStreamSynchronize(user));
-    return RBS_OK;
+    return run_host_pipelined(a, 1, 0, (long)g_pipe.sm_count * 4 * rbs::kBlock, qpos_host, qvel_host, total_steps, launch_body_plane_any);
 }
 
 int rbs_run_two_ball_host(const rbs_two_ball_args *a, void *qpos_host, void *qvel_host, long total_steps) {
     int rc = validate_two_ball(a, false);
     if (rc) return rc;
-    return run_host(a, 2, 0, qpos_host, qvel_host, total_steps, rbs_step_two_ball);
+    rc = pipe_init_locked();
+    if (rc) return rc;
+    return run_host_pipelined(a, 2, 0, (long)g_pipe.sm_count * 8 * rbs::kBlock, qpos_host, qvel_host, total_steps, launch_two_ball_any);
 }
 
 int rbs_run_multi_sphere_host(const rbs_multi_sphere_args *a, void *qpos_host, void *qvel_host, long total_steps) {
     int rc = validate_multi_sphere(a, false);
     if (rc) return rc;
-    return run_host(a, a->n_body, 1, qpos_host, qvel_host, total_steps, rbs_step_multi_sphere);
+    rc = pipe_init_locked();
+    if (rc) return rc;
+    int threads, epb;
+    multi_sphere_shape(a->n_body, &threads, &epb);
+    // one wave = the CTAs resident at once (about five 128-thread CTAs per SM), in environments
+    const long resident = threads <= 256 ? 5 : (threads <= 512 ? 2 : 1);
+    return run_host_pipelined(a, a->n_body, 1, (long)g_pipe.sm_count * resident * epb, qpos_host, qvel_host, total_steps, launch_multi_sphere_any);
 }
 
 int rbs_release_workspace(void) {

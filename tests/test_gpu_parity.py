@@ -330,6 +330,38 @@ def test_cube_golden_fast_policy(rb, golden):
 
 
 # ------------------------------------------------------------------------------------ two balls
+def test_box_compaction_is_bit_identical(rb):
+    """The compacting plane-frame box kernel (step_box_plane_pfc_kernel: hit environments queue their contact work in
+    shared memory and the first `count` threads of the CTA resolve it) runs, per environment, exactly the statements of
+    the thread-per-environment kernel: states and event counters must be the same bits -- bounce and incline (where most
+    of a CTA is hit and the in-place path is taken), fp64 and fp32, ragged sizes, with per-environment parameters."""
+    from rigidbody_simulation_b200 import scenes, stepper, synth
+    dev = torch.device("cuda:0")
+    for kind, E, dtype, per_env in (("bounce", 100_003, np.float64, False), ("incline", 65_536 + 77, np.float64, False),
+                                    ("bounce", 50_001, np.float32, False), ("bounce", 20_000, np.float64, True), ("incline", 90, np.float64, False)):
+        s = synth.cube(E, kind=kind)
+        res = {}
+        for compact in (0, 1):
+            old = rb._lib.set_option("box_compact", compact)
+            try:
+                model = scenes.cube_on_plane(E, theta=s["theta"], device=dev, dtype=tdt(dtype))
+                e, mu = 0.2, 0.6
+                if per_env:
+                    rng = np.random.default_rng(3)
+                    model.set_per_env(restitution=rng.uniform(0.0, 0.6, E), friction=rng.uniform(0.1, 0.9, E))
+                    e = mu = None
+                data = rb.BatchedData(model)
+                data.set_state(s["qpos"], s["qvel"])
+                for K in (4, 130, 66):
+                    stepper.step_body_plane(model, data, -1, s["dt"], e, mu, 1e-4, substeps=K, count=True, arith="fast")
+                res[compact] = state_of(data) + tuple(c.copy() for c in data.counters())
+            finally:
+                rb._lib.set_option("box_compact", old)
+        for a, b in zip(res[0], res[1]):
+            assert np.array_equal(a, b), (kind, E, dtype, per_env)
+        assert res[1][2].sum() > E // 4                        # the horizon does exercise contacts
+
+
 def test_two_ball_golden_and_script(rb, golden):
     from rigidbody_simulation_b200.src.simulation import ball_collision
     s = golden("script_ball_collision_500")
@@ -500,8 +532,9 @@ def test_multi_sphere_tilted_ground_and_mixed_radii_vs_oracle(rb):
             data.set_state(s["qpos"], s["qvel"])
             qp, qv = s["qpos"].reshape(E, B, 7).copy(), s["qvel"].reshape(E, B, 6).copy()
             cnt = (np.zeros((E, B), np.uint32), np.zeros((E, B), np.uint32))
-            okw = dict(mass=m, inertia=I, radius=radii.reshape(E, B), plane_pos=[0, 0, 0], plane_normal=normal, gravity=G, dt=0.01,
-                       restitution=1.0, friction=mu, counters=cnt)
+            assert np.allclose(model.plane_normal, normal, atol=1e-15)
+            okw = dict(mass=m, inertia=I, radius=radii.reshape(E, B), plane_pos=[0, 0, 0], plane_normal=model.plane_normal, gravity=G,
+                       dt=0.01, restitution=1.0, friction=mu, counters=cnt)
             done = 0
             for upto in (1, 10, 40):
                 co.step_multi_sphere(qp, qv, upto - done, **okw)
@@ -509,10 +542,16 @@ def test_multi_sphere_tilted_ground_and_mixed_radii_vs_oracle(rb):
                 done = upto
                 gq, gv = state_of(data)
                 err = max(comp_rel_err(gq.ravel(), qp.ravel(), 1e-3), comp_rel_err(gv.ravel(), qv.ravel(), 1e-3))
+                ev = np.abs(gv.ravel() - qv.ravel()) / np.maximum(np.abs(qv.ravel()), 1e-3)
+                ep = np.abs(gq.ravel() - qp.ravel()) / np.maximum(np.abs(qp.ravel()), 1e-3)
+                iv, ip = int(np.argmax(ev)), int(np.argmax(ep))
+                where = ("qvel", iv // (6 * B), (iv // 6) % B, iv % 6, gv.ravel()[iv], qv.ravel()[iv], float(ev[iv]),
+                         "qpos", ip // (7 * B), (ip // 7) % B, ip % 7, gq.ravel()[ip], qp.ravel()[ip], float(ep[ip]),
+                         "counts", int(cnt[0].sum()), int(cnt[1].sum()))
                 if arith == "strict":
-                    assert err == 0.0, (mu, upto, err)
+                    assert err == 0.0, (mu, upto, err, where)
                 elif upto == 1:
-                    assert err <= F64_STEP, (mu, upto, err)
+                    assert err <= F64_STEP, (mu, upto, err, where)
                 elif upto == 10:
                     assert err <= 1e-9, (mu, upto, err)
                     calls, imps = data.counters()
@@ -1004,6 +1043,46 @@ def test_host_buffer_drivers_two_ball_and_multi_sphere(rb):
     assert (qp_h == gq).all() and (qv_h == gv).all()
     with pytest.raises(ValueError):                       # wrong shape is refused before anything is launched
         stepper.run_multi_sphere_host(model, qp_h[:, :-1].copy(), qv_h, 1)
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_host_buffer_drivers_pipelined_chunks_two_ball_and_multi_sphere(rb, arith):
+    """The two-ball and multi-sphere host-buffer drivers run the same chunk pipeline as the single-body one (whole waves
+    per chunk, copies overlapped with stepping): sizes that need several chunks with a ragged last one, per-environment
+    masses / radii (so the windowed parameter pointers and row strides are exercised), a step count that is not a multiple
+    of the fuse factor -- the call must return exactly what the device-resident path computes with the same launches."""
+    from rigidbody_simulation_b200 import stepper, synth
+    from rigidbody_simulation_b200.src.simulation import ball_collision, multi_sphere_bounce as ms
+    old = rb._lib.set_option("host_chunks", 7)
+    try:
+        E = 500_003
+        s = synth.two_ball(E)
+        model, data = ball_collision.build(E)
+        rng = np.random.default_rng(5)
+        model.set_per_env(mass=torch.tensor(rng.uniform(0.15, 0.3, (2, E)), dtype=torch.float64, device="cuda"),
+                          radius=torch.tensor(rng.uniform(0.09, 0.11, E), dtype=torch.float64, device="cuda"))
+        data.set_state(s["qpos"], s["qvel"])
+        for k in (60, 60, 31):
+            stepper.step_two_ball(model, data, 0.01, 1.0, 0.3, radius=0.1, substeps=k, arith=arith)
+        qp_h, qv_h = s["qpos"].copy(), s["qvel"].copy()
+        stepper.run_two_ball_host(model, qp_h, qv_h, 151, dt=0.01, restitution=1.0, friction=0.3, radius=0.1, substeps=60, arith=arith)
+        gq, gv = state_of(data)
+        assert (qp_h == gq).all() and (qv_h == gv).all()
+        E, B = 5_001, 64
+        s = synth.multi_sphere(E, n_body=B, friction=0.2)
+        model, data = ms.build(E, n_body=B)
+        r = torch.tensor(0.09 + 0.02 * (np.arange(E * B) % 7) / 7, dtype=torch.float64, device="cuda")
+        model.set_per_env(radius=r, mass=torch.full_like(r, float(model.body_mass[1])),
+                          inertia=torch.full((3, E * B), float(model.body_inertia[1][0]), dtype=torch.float64, device="cuda"))
+        data.set_state(s["qpos"], s["qvel"])
+        for k in (16, 16, 5):
+            stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.2, substeps=k, arith=arith)
+        qp_h, qv_h = s["qpos"].copy(), s["qvel"].copy()
+        stepper.run_multi_sphere_host(model, qp_h, qv_h, 37, dt=0.01, restitution=1.0, friction=0.2, substeps=16, arith=arith)
+        gq, gv = state_of(data)
+        assert (qp_h == gq).all() and (qv_h == gv).all()
+    finally:
+        rb._lib.set_option("host_chunks", old)
 
 
 def test_free_functions_follow_input_precision(rb):
