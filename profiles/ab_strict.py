@@ -1,0 +1,53 @@
+"""A/B of the strict (bit-faithful, literal-inertia) single-body stepper's occupancy variants (option strict_minb = 2 /
+4 / 5 / 6 resident CTAs per SM) on configs 2 and 4 (1,048,576 envs, fp64): 512 substeps from the initial state in 4
+launches of 128; one JSON line per run, with a bitwise comparison of the final state against the first variant.
+    python profiles/ab_strict.py
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+import rigidbody_simulation_b200 as rb
+from rigidbody_simulation_b200 import scenes, stepper, synth
+
+dev = torch.device("cuda:0")
+E, K, L = 1 << 20, 128, 4
+for name in ("sphere_incline", "cube_bounce", "cube_incline"):
+    if name == "sphere_incline":
+        s = synth.sphere_incline(E)
+        model = scenes.sphere_on_incline(E, device=dev)
+        model.set_per_env(restitution=s["restitution"], friction=s["friction"])
+        kw = dict(restitution=None, friction_coeff=None, contact_threshold=0.0)
+    else:
+        s = synth.cube(E, kind=name.split("_")[1])
+        model = scenes.cube_on_plane(E, theta=s["theta"], device=dev)
+        kw = dict(restitution=0.2, friction_coeff=0.6, contact_threshold=1e-4)
+    data = rb.BatchedData(model)
+    ref = None
+    for minb in (2, 4, 5, 6):
+        rb._lib.set_option("strict_minb", minb)
+        best = None
+        for rep in range(2):
+            data.set_state(s["qpos"], s["qvel"])
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(L + 1)]
+            for i in range(L):
+                ev[i].record()
+                stepper.step_body_plane(model, data, -1, s["dt"], kw["restitution"], kw["friction_coeff"], kw["contact_threshold"],
+                                        substeps=K, count=False, arith="strict")
+            ev[L].record()
+            torch.cuda.synchronize()
+            ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(L)]
+            if best is None or sum(ms) < sum(best):
+                best = ms
+        same = None
+        if ref is None:
+            ref = data.state.clone()
+        else:
+            same = bool(torch.equal(ref, data.state))
+        print(json.dumps({"config": name, "strict_minb": minb, "launch_ms": [round(m, 3) for m in best],
+                          "env_substeps_per_s": E * K * L / (sum(best) * 1e-3), "state_bitwise_equal_to_first_variant": same}), flush=True)
+rb._lib.set_option("strict_minb", 2)

@@ -49,12 +49,13 @@ Option g_options[] = {
     {"minb", "RBS_MINB", {0}, 0},                            // resident CTAs per SM of the sphere steppers (0 = tuned default)
     {"pf_min_substeps", "RBS_PF_MIN_SUBSTEPS", {0}, 4},      // shortest launch that takes the plane-frame kernels
     {"pf_packed", "RBS_PF_PACKED", {0}, 1},                  // float sphere stepper: packed fp32x2 kernel (1) or scalar (0)
+    {"strict_minb", "RBS_STRICT_MINB", {0}, 2},              // resident CTAs per SM of the strict literal-inertia stepper (2, 4, 5, 6)
     {"box_minb", "RBS_BOX_MINB", {0}, 6},                    // resident CTAs per SM of the plane-frame box kernel
     {"box_compact", "RBS_BOX_COMPACT", {0}, 0},              // plane-frame box kernel: CTA-level compaction of contacts (measured slower: off)
     {"tb_minb", "RBS_TB_MINB", {0}, 0},                      // resident CTAs per SM of the two-ball fast kernel (5, 6 or 8; 0 = 6 in double, 8 in float)
     {"ms_skin_percent", "RBS_MS_SKIN_PERCENT", {0}, 50},     // starting skin of the adaptive partner lists
     {"ms_kernel", "RBS_MS_KERNEL", {0}, 2},                  // multi-sphere fast policy: 2 = plane-frame kernel, 1 = first generation
-    {"ms_walk_cost", "RBS_MS_WALK_COST", {0}, 16},           // plane-frame multi-sphere kernel: cost of a list entry per substep (skin controller)
+    {"ms_walk_cost", "RBS_MS_WALK_COST", {0}, 20},           // plane-frame multi-sphere kernel: cost of a list entry per substep (skin controller)
     {"probe_mode", "RBS_PROBE_MODE", {0}, 1},                // rbs_fma_probe operand mode
     {"host_chunks", "RBS_HOST_CHUNKS", {0}, 16},             // pipeline depth of rbs_run_body_plane_host
 };
@@ -202,6 +203,15 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
         }
         rbs::step_body_plane_kernel<T, GEOM, SCHEME, 1, 4><<<grid, rbs::kBlock, 0, st>>>(p);
     } else {
+        // literal inv(R diag(I) R^T): resident CTAs per SM (register cap 255 / 128 / 96 / 80) -- option strict_minb
+        if constexpr (SCHEME == 0) {
+            switch ((int)option("strict_minb")) {
+                case 4: rbs::step_body_plane_kernel<T, GEOM, SCHEME, 0, 4><<<grid, rbs::kBlock, 0, st>>>(p); return;
+                case 5: rbs::step_body_plane_kernel<T, GEOM, SCHEME, 0, 5><<<grid, rbs::kBlock, 0, st>>>(p); return;
+                case 6: rbs::step_body_plane_kernel<T, GEOM, SCHEME, 0, 6><<<grid, rbs::kBlock, 0, st>>>(p); return;
+                default: break;
+            }
+        }
         rbs::step_body_plane_kernel<T, GEOM, SCHEME, 0, 2><<<grid, rbs::kBlock, 0, st>>>(p);
     }
 }
