@@ -603,7 +603,11 @@ int pipe_init() {
     return RBS_OK;
 }
 
-int pipe_init_locked() {
+// argument checks shared by the host-buffer drivers, then the pipeline resources; 1 = nothing to do
+int host_driver_prologue(long n_env, const void *qpos_host, const void *qvel_host, long total_steps) {
+    if (total_steps < 0) return fail(RBS_EINVAL, "total_steps %ld < 0", total_steps);
+    if (n_env == 0) return 1;
+    if (!qpos_host || !qvel_host) return fail(RBS_EINVAL, "null host buffer");
     std::lock_guard<std::mutex> lock(g_ws_mutex);
     return pipe_init();
 }
@@ -900,24 +904,24 @@ int rbs_run_body_plane_host(const rbs_body_plane_args *a, void *qpos_host, void 
     int rc = validate_body_plane(a, false);
     if (rc) return rc;
     if (a->trajectory) return fail(RBS_EINVAL, "rbs_run_body_plane_host: trajectory sampling needs device-resident stepping");
-    rc = pipe_init_locked();
-    if (rc) return rc;
+    rc = host_driver_prologue(a->n_env, qpos_host, qvel_host, total_steps);
+    if (rc) return rc < 0 ? rc : RBS_OK;
     return run_host_pipelined(a, 1, 0, (long)g_pipe.sm_count * 4 * rbs::kBlock, qpos_host, qvel_host, total_steps, launch_body_plane_any);
 }
 
 int rbs_run_two_ball_host(const rbs_two_ball_args *a, void *qpos_host, void *qvel_host, long total_steps) {
     int rc = validate_two_ball(a, false);
     if (rc) return rc;
-    rc = pipe_init_locked();
-    if (rc) return rc;
+    rc = host_driver_prologue(a->n_env, qpos_host, qvel_host, total_steps);
+    if (rc) return rc < 0 ? rc : RBS_OK;
     return run_host_pipelined(a, 2, 0, (long)g_pipe.sm_count * 8 * rbs::kBlock, qpos_host, qvel_host, total_steps, launch_two_ball_any);
 }
 
 int rbs_run_multi_sphere_host(const rbs_multi_sphere_args *a, void *qpos_host, void *qvel_host, long total_steps) {
     int rc = validate_multi_sphere(a, false);
     if (rc) return rc;
-    rc = pipe_init_locked();
-    if (rc) return rc;
+    rc = host_driver_prologue(a->n_env, qpos_host, qvel_host, total_steps);
+    if (rc) return rc < 0 ? rc : RBS_OK;
     int threads, epb;
     multi_sphere_shape(a->n_body, &threads, &epb);
     // one wave = the CTAs resident at once (about five 128-thread CTAs per SM), in environments
