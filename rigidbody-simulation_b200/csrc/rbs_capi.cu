@@ -49,7 +49,7 @@ Option g_options[] = {
     {"minb", "RBS_MINB", {0}, 0},                            // resident CTAs per SM of the sphere steppers (0 = tuned default)
     {"pf_min_substeps", "RBS_PF_MIN_SUBSTEPS", {0}, 4},      // shortest launch that takes the plane-frame kernels
     {"pf_packed", "RBS_PF_PACKED", {0}, 1},                  // float sphere stepper: packed fp32x2 kernel (1) or scalar (0)
-    {"strict_minb", "RBS_STRICT_MINB", {0}, 2},              // resident CTAs per SM of the strict literal-inertia stepper (2, 4, 5, 6)
+    {"strict_minb", "RBS_STRICT_MINB", {0}, 0},              // resident CTAs per SM of the strict literal-inertia stepper (2, 4, 5, 6; 0 = tuned)
     {"box_minb", "RBS_BOX_MINB", {0}, 6},                    // resident CTAs per SM of the plane-frame box kernel
     {"box_compact", "RBS_BOX_COMPACT", {0}, 0},              // plane-frame box kernel: CTA-level compaction of contacts (measured slower: off)
     {"tb_minb", "RBS_TB_MINB", {0}, 0},                      // resident CTAs per SM of the two-ball fast kernel (5, 6 or 8; 0 = 6 in double, 8 in float)
@@ -205,7 +205,10 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
     } else {
         // literal inv(R diag(I) R^T): resident CTAs per SM (register cap 255 / 128 / 96 / 80) -- option strict_minb
         if constexpr (SCHEME == 0) {
-            switch ((int)option("strict_minb")) {
+            // 0 = measured best on B200 (profiles/r2_ab_strict.jsonl: +14 % sphere, +25-28 % cube over the uncapped build)
+            int minb = (int)option("strict_minb");
+            if (minb == 0) minb = GEOM == 0 ? 5 : 4;
+            switch (minb) {
                 case 4: rbs::step_body_plane_kernel<T, GEOM, SCHEME, 0, 4><<<grid, rbs::kBlock, 0, st>>>(p); return;
                 case 5: rbs::step_body_plane_kernel<T, GEOM, SCHEME, 0, 5><<<grid, rbs::kBlock, 0, st>>>(p); return;
                 case 6: rbs::step_body_plane_kernel<T, GEOM, SCHEME, 0, 6><<<grid, rbs::kBlock, 0, st>>>(p); return;

@@ -79,6 +79,23 @@ def _parse_cpulist(text):
     return cpus
 
 
+def _nvml_cpu_affinity(bdf):
+    """CPUs the NVIDIA driver reports as local to the GPU at PCI address ``bdf`` (empty set when NVML cannot say)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(("0000" + bdf).encode() if len(bdf.split(":")[0]) == 4 else bdf.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, 16)
+        cpus = set()
+        for i, w in enumerate(words):
+            for bit in range(64):
+                if (int(w) >> bit) & 1:
+                    cpus.add(64 * i + bit)
+        return cpus
+    except Exception:
+        return set()
+
+
 def bind_to_gpu_numa(device_index):
     """Pin the calling thread (and every thread it starts afterwards) to the CPUs of the NUMA node that GPU
     ``device_index`` hangs off, so that pinned host buffers allocated from now on are first-touched in the memory next
@@ -99,6 +116,12 @@ def bind_to_gpu_numa(device_index):
         cpus = local & allowed
         info["allowed_cpus"] = len(allowed)
         if info["numa_node"] < 0 or not cpus or cpus == allowed:
+            # sysfs has no locality (typical inside a VM): ask the driver for the GPU's ideal CPU set instead
+            nv = _nvml_cpu_affinity(bdf)
+            if nv:
+                info["source"] = "nvml"
+                cpus = nv & allowed
+        if not cpus or cpus == allowed:
             info["note"] = "single NUMA domain (or no locality information): nothing to bind"
             return info
         os.sched_setaffinity(0, cpus)
