@@ -542,77 +542,87 @@ int launch_multi_sphere_any(const rbs_multi_sphere_args *a, const Window &w) {
     return check_launch("rbs_step_multi_sphere");
 }
 
-// cached device workspace of the host-buffer drivers -------------------------------------------
-std::mutex g_ws_mutex;
-void *g_ws = nullptr;
-size_t g_ws_bytes = 0;
+// Host-buffer driver resources, ONE SET PER DEVICE: a cached device workspace and the streams / events of the chunk
+// pipeline, created at the first host-buffer call made with that device current.  Calls on different devices share
+// nothing and run concurrently; calls on the same device are serialised by that device's mutex (they would contend for
+// the same copy engines anyway).  Nothing else in the library keeps state between calls.
+constexpr int kMaxChunks = 32;
+constexpr int kMaxDevices = 64;
+struct Pipe {
+    std::mutex mutex;
+    bool ready = false;
+    int sm_count = 148;
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+    cudaStream_t in = nullptr, out = nullptr, compute[2] = {nullptr, nullptr};
+    cudaEvent_t start = nullptr, finished = nullptr, arrived[kMaxChunks] = {}, stepped[kMaxChunks] = {};
+};
+Pipe g_pipes[kMaxDevices];
 
-int workspace(size_t bytes, void **out) {
-    if (bytes > g_ws_bytes) {
-        if (g_ws) cudaFree(g_ws);
-        g_ws = nullptr;
-        g_ws_bytes = 0;
-        cudaError_t err = cudaMalloc(&g_ws, bytes);
+int workspace(Pipe &pp, size_t bytes, void **out) {
+    if (bytes > pp.ws_bytes) {
+        if (pp.ws) cudaFree(pp.ws);
+        pp.ws = nullptr;
+        pp.ws_bytes = 0;
+        cudaError_t err = cudaMalloc(&pp.ws, bytes);
         if (err != cudaSuccess) {
             cudaGetLastError();
             return fail(err == cudaErrorMemoryAllocation ? RBS_ENOMEM : RBS_ECUDA, "workspace of %zu bytes: %s", bytes,
                         cudaGetErrorString(err));
         }
-        g_ws_bytes = bytes;
+        pp.ws_bytes = bytes;
     }
-    *out = g_ws;
+    *out = pp.ws;
     return RBS_OK;
 }
 
-// streams / events of the pipelined host driver (created once per process) ---------------------------------
-constexpr int kMaxChunks = 32;
-struct Pipe {
-    bool ready = false;
-    int device = -1;
-    int sm_count = 148;
-    cudaStream_t in = nullptr, out = nullptr, compute[2] = {nullptr, nullptr};
-    cudaEvent_t start = nullptr, finished = nullptr, arrived[kMaxChunks] = {}, stepped[kMaxChunks] = {};
-} g_pipe;
-
-// One process drives one GPU: the driver's streams and workspace live on the device that was
-// current at the first host-buffer call, and a call made with another device current is refused.
-int pipe_init() {
+// the current device's pipeline (nullptr + error when there is no usable device)
+Pipe *current_pipe() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) {
         cudaGetLastError();
-        return fail(RBS_ECUDA, "no CUDA device");
+        fail(RBS_ECUDA, "no CUDA device");
+        return nullptr;
     }
-    if (g_pipe.ready) {
-        if (dev != g_pipe.device)
-            return fail(RBS_EINVAL, "host-buffer driver is bound to device %d of this process, current device is %d", g_pipe.device, dev);
-        return RBS_OK;
+    if (dev < 0 || dev >= kMaxDevices) {
+        fail(RBS_EINVAL, "device ordinal %d outside 0..%d", dev, kMaxDevices - 1);
+        return nullptr;
     }
+    return &g_pipes[dev];
+}
+
+// call with pp.mutex held
+int pipe_init(Pipe &pp) {
+    if (pp.ready) return RBS_OK;
+    int dev = 0;
+    cudaGetDevice(&dev);
     cudaError_t err = cudaSuccess;
     auto ok = [&](cudaError_t e) { if (err == cudaSuccess) err = e; };
-    ok(cudaDeviceGetAttribute(&g_pipe.sm_count, cudaDevAttrMultiProcessorCount, dev));
-    ok(cudaStreamCreateWithFlags(&g_pipe.in, cudaStreamNonBlocking));
-    ok(cudaStreamCreateWithFlags(&g_pipe.out, cudaStreamNonBlocking));
-    ok(cudaStreamCreateWithFlags(&g_pipe.compute[0], cudaStreamNonBlocking));
-    ok(cudaStreamCreateWithFlags(&g_pipe.compute[1], cudaStreamNonBlocking));
-    ok(cudaEventCreateWithFlags(&g_pipe.start, cudaEventDisableTiming));
-    ok(cudaEventCreateWithFlags(&g_pipe.finished, cudaEventDisableTiming));
+    ok(cudaDeviceGetAttribute(&pp.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    ok(cudaStreamCreateWithFlags(&pp.in, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&pp.out, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&pp.compute[0], cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&pp.compute[1], cudaStreamNonBlocking));
+    ok(cudaEventCreateWithFlags(&pp.start, cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&pp.finished, cudaEventDisableTiming));
     for (int i = 0; i < kMaxChunks; ++i) {
-        ok(cudaEventCreateWithFlags(&g_pipe.arrived[i], cudaEventDisableTiming));
-        ok(cudaEventCreateWithFlags(&g_pipe.stepped[i], cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&pp.arrived[i], cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&pp.stepped[i], cudaEventDisableTiming));
     }
-    if (err != cudaSuccess) return fail(RBS_ECUDA, "pipeline resources: %s", cudaGetErrorString(err));
-    g_pipe.device = dev;
-    g_pipe.ready = true;
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(RBS_ECUDA, "pipeline resources: %s", cudaGetErrorString(err));
+    }
+    pp.ready = true;
     return RBS_OK;
 }
 
-// argument checks shared by the host-buffer drivers, then the pipeline resources; 1 = nothing to do
+// argument checks shared by the host-buffer drivers; 1 = nothing to do
 int host_driver_prologue(long n_env, const void *qpos_host, const void *qvel_host, long total_steps) {
     if (total_steps < 0) return fail(RBS_EINVAL, "total_steps %ld < 0", total_steps);
     if (n_env == 0) return 1;
     if (!qpos_host || !qvel_host) return fail(RBS_EINVAL, "null host buffer");
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    return pipe_init();
+    return RBS_OK;
 }
 
 #define RBS_CUDA(call)                                                                   \
@@ -628,19 +638,22 @@ int host_driver_prologue(long n_env, const void *qpos_host, const void *qvel_hos
 // last chunk are one quantum; the ones in between share the rest (at most `host_chunks` chunks, option of that name).
 // `launch(local_args, window)` enqueues one launch of local_args->substeps substeps on the window's stream.
 template <typename Args, typename LaunchFn>
-int run_host_pipelined(const Args *a, int n_body, int body_fastest, long quantum, void *qpos_host, void *qvel_host,
+int run_host_pipelined(const Args *a, int n_body, int body_fastest, long envs_per_sm_wave, void *qpos_host, void *qvel_host,
                        long total_steps, LaunchFn launch) {
-    if (total_steps < 0) return fail(RBS_EINVAL, "total_steps %ld < 0", total_steps);
-    if (a->n_env == 0) return RBS_OK;
-    if (!qpos_host || !qvel_host) return fail(RBS_EINVAL, "null host buffer");
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    int rc = pipe_init();
+    int rc = host_driver_prologue(a->n_env, qpos_host, qvel_host, total_steps);
+    if (rc) return rc < 0 ? rc : RBS_OK;
+    Pipe *pipe = current_pipe();
+    if (!pipe) return RBS_ECUDA;
+    Pipe &g_pipe = *pipe;
+    std::lock_guard<std::mutex> lock(g_pipe.mutex);
+    rc = pipe_init(g_pipe);
     if (rc) return rc;
+    long quantum = (long)g_pipe.sm_count * envs_per_sm_wave;
     const size_t es = elem_size(a->dtype);
     const long E = a->n_env;
     const size_t per_env = (size_t)n_body * es;              // bytes of one scalar row entry group per environment
     void *base = nullptr;
-    rc = workspace((size_t)E * 26 * per_env, &base);
+    rc = workspace(g_pipe, (size_t)E * 26 * per_env, &base);
     if (rc) return rc;
     char *qpos_d = static_cast<char *>(base), *qvel_d = qpos_d + (size_t)E * 7 * per_env, *state_d = qvel_d + (size_t)E * 6 * per_env;
     long max_chunks = option("host_chunks");
@@ -907,36 +920,32 @@ int rbs_run_body_plane_host(const rbs_body_plane_args *a, void *qpos_host, void 
     int rc = validate_body_plane(a, false);
     if (rc) return rc;
     if (a->trajectory) return fail(RBS_EINVAL, "rbs_run_body_plane_host: trajectory sampling needs device-resident stepping");
-    rc = host_driver_prologue(a->n_env, qpos_host, qvel_host, total_steps);
-    if (rc) return rc < 0 ? rc : RBS_OK;
-    return run_host_pipelined(a, 1, 0, (long)g_pipe.sm_count * 4 * rbs::kBlock, qpos_host, qvel_host, total_steps, launch_body_plane_any);
+    return run_host_pipelined(a, 1, 0, 4L * rbs::kBlock, qpos_host, qvel_host, total_steps, launch_body_plane_any);
 }
 
 int rbs_run_two_ball_host(const rbs_two_ball_args *a, void *qpos_host, void *qvel_host, long total_steps) {
     int rc = validate_two_ball(a, false);
     if (rc) return rc;
-    rc = host_driver_prologue(a->n_env, qpos_host, qvel_host, total_steps);
-    if (rc) return rc < 0 ? rc : RBS_OK;
-    return run_host_pipelined(a, 2, 0, (long)g_pipe.sm_count * 8 * rbs::kBlock, qpos_host, qvel_host, total_steps, launch_two_ball_any);
+    return run_host_pipelined(a, 2, 0, 8L * rbs::kBlock, qpos_host, qvel_host, total_steps, launch_two_ball_any);
 }
 
 int rbs_run_multi_sphere_host(const rbs_multi_sphere_args *a, void *qpos_host, void *qvel_host, long total_steps) {
     int rc = validate_multi_sphere(a, false);
     if (rc) return rc;
-    rc = host_driver_prologue(a->n_env, qpos_host, qvel_host, total_steps);
-    if (rc) return rc < 0 ? rc : RBS_OK;
     int threads, epb;
     multi_sphere_shape(a->n_body, &threads, &epb);
     // one wave = the CTAs resident at once (about five 128-thread CTAs per SM), in environments
     const long resident = threads <= 256 ? 5 : (threads <= 512 ? 2 : 1);
-    return run_host_pipelined(a, a->n_body, 1, (long)g_pipe.sm_count * resident * epb, qpos_host, qvel_host, total_steps, launch_multi_sphere_any);
+    return run_host_pipelined(a, a->n_body, 1, resident * epb, qpos_host, qvel_host, total_steps, launch_multi_sphere_any);
 }
 
 int rbs_release_workspace(void) {
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    if (g_ws) cudaFree(g_ws);
-    g_ws = nullptr;
-    g_ws_bytes = 0;
+    Pipe *pipe = current_pipe();          // the workspace of the CURRENT device
+    if (!pipe) return RBS_OK;
+    std::lock_guard<std::mutex> lock(pipe->mutex);
+    if (pipe->ws) cudaFree(pipe->ws);
+    pipe->ws = nullptr;
+    pipe->ws_bytes = 0;
     return RBS_OK;
 }
 
