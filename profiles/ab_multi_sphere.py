@@ -24,7 +24,7 @@ for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
         for mu in (0.0, 0.3):
             s = synth.multi_sphere(E, n_body=64, friction=mu)
             for kernel in (1, 2):
-                for walk in ((20,) if kernel == 1 else (10, 20, 40)):
+                for walk in ((20,) if kernel == 1 else (20, 40, 80)):
                     rb._lib.set_option("ms_kernel", kernel)
                     rb._lib.set_option("ms_walk_cost", walk)
                     model, data = multi_sphere_bounce.build(E, device=dev, dtype=dtype, n_body=64)

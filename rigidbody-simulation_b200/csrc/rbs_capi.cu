@@ -55,7 +55,7 @@ Option g_options[] = {
     {"tb_minb", "RBS_TB_MINB", {0}, 0},                      // resident CTAs per SM of the two-ball fast kernel (5, 6 or 8; 0 = 6 in double, 8 in float)
     {"ms_skin_percent", "RBS_MS_SKIN_PERCENT", {0}, 50},     // starting skin of the adaptive partner lists
     {"ms_kernel", "RBS_MS_KERNEL", {0}, 2},                  // multi-sphere fast policy: 2 = plane-frame kernel, 1 = first generation
-    {"ms_walk_cost", "RBS_MS_WALK_COST", {0}, 20},           // plane-frame multi-sphere kernel: cost of a list entry per substep (skin controller)
+    {"ms_walk_cost", "RBS_MS_WALK_COST", {0}, 40},           // plane-frame multi-sphere kernel: cost of a list entry per substep (skin controller)
     {"probe_mode", "RBS_PROBE_MODE", {0}, 1},                // rbs_fma_probe operand mode
     {"host_chunks", "RBS_HOST_CHUNKS", {0}, 16},             // pipeline depth of rbs_run_body_plane_host
 };
