@@ -41,7 +41,7 @@ CONFIGS = {
     "cube_incline": dict(baseline="configs[3]", envs=1 << 20, bodies=1, fuse=128, scaling="weak",
                          workload="cube_incline_1M: models/cube.xml, plane and cube tilted 0.7 rad, shipped pose + perturbation, "
                                   "from rest (2-4 contacts per step), e=0.2, mu=0.6, thr=1e-4, dt=0.009 (BASELINE configs[3])"),
-    "multi_sphere64": dict(baseline="configs[4]", envs=1 << 16, bodies=64, fuse=128, scaling="strong",
+    "multi_sphere64": dict(baseline="configs[4]", envs=1 << 16, bodies=64, fuse=256, scaling="strong",
                            workload="multi_sphere64_65k: models/multi_sphere.xml scaled to 64 spheres per env (r=0.1) on a jittered "
                                     "4x4x4 lattice, all-pairs contacts, e=1.0, mu=0.0, dt=0.01; 65,536 envs IN TOTAL sharded over the "
                                     "GPUs (BASELINE configs[4])"),
