@@ -51,3 +51,52 @@ for name in ("sphere_incline", "cube_bounce", "cube_incline"):
         print(json.dumps({"config": name, "strict_minb": minb, "launch_ms": [round(m, 3) for m in best],
                           "env_substeps_per_s": E * K * L / (sum(best) * 1e-3), "state_bitwise_equal_to_first_variant": same}), flush=True)
 rb._lib.set_option("strict_minb", 0)
+
+# strict two-ball (config 3) and strict multi-sphere (config 5, 8,192 envs) ----------------------------------------------
+from rigidbody_simulation_b200.src.simulation import ball_collision, multi_sphere_bounce
+
+s = synth.two_ball(E)
+model, data = ball_collision.build(E, device=dev)
+ref = None
+for minb in (3, 4, 5):
+    rb._lib.set_option("strict_tb_minb", minb)
+    best = None
+    for rep in range(2):
+        data.set_state(s["qpos"], s["qvel"])
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(L + 1)]
+        for i in range(L):
+            ev[i].record()
+            stepper.step_two_ball(model, data, 0.01, 1.0, 0.3, radius=0.1, substeps=K, count=False, arith="strict")
+        ev[L].record()
+        torch.cuda.synchronize()
+        ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(L)]
+        if best is None or sum(ms) < sum(best):
+            best = ms
+    same = None if ref is None else bool(torch.equal(ref, data.state))
+    ref = data.state.clone() if ref is None else ref
+    print(json.dumps({"config": "two_ball", "strict_tb_minb": minb, "launch_ms": [round(m, 3) for m in best],
+                      "env_substeps_per_s": E * K * L / (sum(best) * 1e-3), "state_bitwise_equal_to_first_variant": same}), flush=True)
+rb._lib.set_option("strict_tb_minb", 0)
+E5 = 8192
+s = synth.multi_sphere(E5, n_body=64, friction=0.0)
+model, data = multi_sphere_bounce.build(E5, device=dev, n_body=64)
+ref = None
+for regs in (168, 128, 96):
+    rb._lib.set_option("strict_ms_regs", regs)
+    best = None
+    for rep in range(2):
+        data.set_state(s["qpos"], s["qvel"])
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(L + 1)]
+        for i in range(L):
+            ev[i].record()
+            stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.0, substeps=K, count=False, arith="strict")
+        ev[L].record()
+        torch.cuda.synchronize()
+        ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(L)]
+        if best is None or sum(ms) < sum(best):
+            best = ms
+    same = None if ref is None else bool(torch.equal(ref, data.state))
+    ref = data.state.clone() if ref is None else ref
+    print(json.dumps({"config": "multi_sphere64_8192", "strict_ms_regs": regs, "launch_ms": [round(m, 3) for m in best],
+                      "body_substeps_per_s": E5 * 64 * K * L / (sum(best) * 1e-3), "state_bitwise_equal_to_first_variant": same}), flush=True)
+rb._lib.set_option("strict_ms_regs", 0)

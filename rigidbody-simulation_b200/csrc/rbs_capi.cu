@@ -50,6 +50,8 @@ Option g_options[] = {
     {"pf_min_substeps", "RBS_PF_MIN_SUBSTEPS", {0}, 4},      // shortest launch that takes the plane-frame kernels
     {"pf_packed", "RBS_PF_PACKED", {0}, 1},                  // float sphere stepper: packed fp32x2 kernel (1) or scalar (0)
     {"strict_minb", "RBS_STRICT_MINB", {0}, 0},              // resident CTAs per SM of the strict literal-inertia stepper (2, 4, 5, 6; 0 = tuned)
+    {"strict_tb_minb", "RBS_STRICT_TB_MINB", {0}, 0},        // resident CTAs per SM of the strict two-ball stepper (3, 4, 5; 0 = tuned)
+    {"strict_ms_regs", "RBS_STRICT_MS_REGS", {0}, 0},        // register cap of the strict literal-inertia multi-sphere stepper (168, 128, 96; 0 = tuned)
     {"box_minb", "RBS_BOX_MINB", {0}, 6},                    // resident CTAs per SM of the plane-frame box kernel
     {"box_compact", "RBS_BOX_COMPACT", {0}, 0},              // plane-frame box kernel: CTA-level compaction of contacts (measured slower: off)
     {"tb_minb", "RBS_TB_MINB", {0}, 0},                      // resident CTAs per SM of the two-ball fast kernel (5, 6 or 8; 0 = 6 in double, 8 in float)
@@ -495,7 +497,12 @@ template <typename T> int launch_multi_sphere(const rbs_multi_sphere_args *a, co
         return RBS_OK;
     }
     if (threads <= 256) {
+        // register cap of the 256-thread class (option strict_ms_regs; 0 = measured best, profiles/r2_ab_strict.jsonl)
+        int regs = (int)option("strict_ms_regs");
+        if (regs == 0) regs = 128;
         if (iso) RBS_MS_LAUNCH((rbs::step_multi_sphere_kernel<T, 1, 256>));
+        else if (regs <= 96) RBS_MS_LAUNCH((rbs::step_multi_sphere_kernel<T, 0, 256, 96>));
+        else if (regs <= 128) RBS_MS_LAUNCH((rbs::step_multi_sphere_kernel<T, 0, 256, 128>));
         else RBS_MS_LAUNCH((rbs::step_multi_sphere_kernel<T, 0, 256>));
     } else if (threads <= 512) {
         if (iso) RBS_MS_LAUNCH((rbs::step_multi_sphere_kernel<T, 1, 512>));
@@ -528,10 +535,19 @@ int launch_two_ball_any(const rbs_two_ball_args *a, const Window &w) {
         else { if (gz) RBS_TB_MINB(float, true); else RBS_TB_MINB(float, false); }
 #undef RBS_TB_MINB
 #undef RBS_TB
-    } else if (a->dtype == RBS_F64) {
-        rbs::step_two_ball_kernel<double><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a, w));
     } else {
-        rbs::step_two_ball_kernel<float><<<grid, rbs::kBlock, 0, st>>>(make_params<float>(a, w));
+        // strict policy: resident CTAs per SM (option strict_tb_minb: 3 = uncapped, 4 = 128 registers, 5 = 96; 0 = measured best)
+        int minb = (int)option("strict_tb_minb");
+        if (minb == 0) minb = 4;
+        if (a->dtype == RBS_F64) {
+            if (minb >= 5) rbs::step_two_ball_kernel<double, 5><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a, w));
+            else if (minb == 4) rbs::step_two_ball_kernel<double, 4><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a, w));
+            else rbs::step_two_ball_kernel<double, 3><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a, w));
+        } else {
+            if (minb >= 5) rbs::step_two_ball_kernel<float, 5><<<grid, rbs::kBlock, 0, st>>>(make_params<float>(a, w));
+            else if (minb == 4) rbs::step_two_ball_kernel<float, 4><<<grid, rbs::kBlock, 0, st>>>(make_params<float>(a, w));
+            else rbs::step_two_ball_kernel<float, 3><<<grid, rbs::kBlock, 0, st>>>(make_params<float>(a, w));
+        }
     }
     return check_launch("rbs_step_two_ball");
 }
