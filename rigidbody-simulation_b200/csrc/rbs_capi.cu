@@ -538,7 +538,7 @@ int launch_two_ball_any(const rbs_two_ball_args *a, const Window &w) {
     } else {
         // strict policy: resident CTAs per SM (option strict_tb_minb: 3 = uncapped, 4 = 128 registers, 5 = 96; 0 = measured best)
         int minb = (int)option("strict_tb_minb");
-        if (minb == 0) minb = 4;
+        if (minb == 0) minb = 5;               // profiles/r2_ab_strict.jsonl: 9.1e10 (uncapped) -> 1.03e11 (128) -> 1.08e11 (96 registers)
         if (a->dtype == RBS_F64) {
             if (minb >= 5) rbs::step_two_ball_kernel<double, 5><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a, w));
             else if (minb == 4) rbs::step_two_ball_kernel<double, 4><<<grid, rbs::kBlock, 0, st>>>(make_params<double>(a, w));
@@ -676,14 +676,16 @@ int run_host_pipelined(const Args *a, int n_body, int body_fastest, long envs_pe
     if (max_chunks < 3) max_chunks = 3;
     if (max_chunks > kMaxChunks) max_chunks = kMaxChunks;
     if (quantum < 1) quantum = 1;
+    // the two exposed chunks (first copy-in, last copy-out) are half a wave: the pipeline fills and drains sooner
+    long edge = (long)g_pipe.sm_count * (envs_per_sm_wave >= 2 ? envs_per_sm_wave / 2 : 1);
     long offs[kMaxChunks + 1];
     int n_chunks = 0;
     offs[0] = 0;
     if (E <= 3 * quantum) {
         offs[++n_chunks] = E;
     } else {
-        offs[++n_chunks] = quantum;
-        const long middle = E - 2 * quantum;
+        offs[++n_chunks] = edge;
+        const long middle = E - 2 * edge;
         const long n_mid = max_chunks - 2;
         long per = (middle + n_mid - 1) / n_mid;
         per = ((per + quantum - 1) / quantum) * quantum;
