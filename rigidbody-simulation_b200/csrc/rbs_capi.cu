@@ -50,6 +50,7 @@ Option g_options[] = {
     {"pf_min_substeps", "RBS_PF_MIN_SUBSTEPS", {0}, 4},      // shortest launch that takes the plane-frame kernels
     {"pf_packed", "RBS_PF_PACKED", {0}, 1},                  // float sphere stepper: packed fp32x2 kernel (1) or scalar (0)
     {"strict_minb", "RBS_STRICT_MINB", {0}, 0},              // resident CTAs per SM of the strict literal-inertia stepper (2, 4, 5, 6; 0 = tuned)
+    {"strict_compact", "RBS_STRICT_COMPACT", {0}, 4},        // strict single-body stepper: 0 = thread per environment, 4 / 5 = CTA-compacted contact path at 4 / 5 resident CTAs
     {"strict_tb_minb", "RBS_STRICT_TB_MINB", {0}, 0},        // resident CTAs per SM of the strict two-ball stepper (3, 4, 5; 0 = tuned)
     {"strict_ms_regs", "RBS_STRICT_MS_REGS", {0}, 0},        // register cap of the strict literal-inertia multi-sphere stepper (168, 128, 96; 0 = tuned)
     {"box_minb", "RBS_BOX_MINB", {0}, 6},                    // resident CTAs per SM of the plane-frame box kernel
@@ -205,6 +206,20 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
         }
         rbs::step_body_plane_kernel<T, GEOM, SCHEME, 1, 4><<<grid, rbs::kBlock, 0, st>>>(p);
     } else {
+        if constexpr (SCHEME == 0) {
+            // the contact path compacted across the CTA (bit-identical results; strict_compact = 0 keeps one environment's
+            // whole substep in its own thread).  Not with an applied wrench: then every lane builds the inverse anyway.
+            if (!a->xfrc && option("strict_compact") != 0) {
+                if (option("strict_compact") >= 5) {
+                    cudaFuncSetAttribute(rbs::step_body_plane_compact_kernel<T, GEOM, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                    rbs::step_body_plane_compact_kernel<T, GEOM, 5><<<grid, rbs::kBlock, 0, st>>>(p);
+                } else {
+                    cudaFuncSetAttribute(rbs::step_body_plane_compact_kernel<T, GEOM, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                    rbs::step_body_plane_compact_kernel<T, GEOM, 4><<<grid, rbs::kBlock, 0, st>>>(p);
+                }
+                return;
+            }
+        }
         // literal inv(R diag(I) R^T): resident CTAs per SM (register cap 255 / 128 / 96 / 80) -- option strict_minb
         if constexpr (SCHEME == 0) {
             // 0 = measured best on B200 (profiles/r2_ab_strict.jsonl: +14 % sphere, +25-28 % cube over the uncapped build)

@@ -362,6 +362,53 @@ def test_box_compaction_is_bit_identical(rb):
         assert res[1][2].sum() > E // 4                        # the horizon does exercise contacts
 
 
+def test_strict_compaction_is_bit_identical(rb):
+    """The strict single-body stepper with its contact path compacted across the CTA (step_body_plane_compact_kernel:
+    every thread parks its state in shared memory, the first `count` threads resolve the queued environments) runs, per
+    environment, exactly the statements of the thread-per-environment kernel: states and event counters must be the same
+    bits -- sphere and cube, fp64 and fp32, ragged sizes, per-environment parameters -- and, like it, bit for bit the oracle."""
+    from rigidbody_simulation_b200 import scenes, stepper, synth
+    dev = torch.device("cuda:0")
+    cases = (("sphere", 100_003, np.float64), ("bounce", 50_001, np.float64), ("incline", 33_000, np.float64),
+             ("sphere", 20_001, np.float32), ("bounce", 20_000, np.float32), ("sphere", 77, np.float64))
+    for kind, E, dtype in cases:
+        if kind == "sphere":
+            s = synth.sphere_incline(E)
+            build = lambda: scenes.sphere_on_incline(E, device=dev, dtype=tdt(dtype))
+            e, mu, thr = s["restitution"], s["friction"], 0.0
+        else:
+            s = synth.cube(E, kind=kind)
+            build = lambda: scenes.cube_on_plane(E, theta=s["theta"], device=dev, dtype=tdt(dtype))
+            rng = np.random.default_rng(4)
+            e, mu, thr = rng.uniform(0.0, 0.5, E), rng.uniform(0.2, 0.9, E), 1e-4
+        res = {}
+        for compact in (0, 4, 5):
+            old = rb._lib.set_option("strict_compact", compact)
+            try:
+                model = build()
+                model.set_per_env(restitution=e, friction=mu)
+                data = rb.BatchedData(model)
+                data.set_state(s["qpos"], s["qvel"])
+                for K in (1, 90, 37):
+                    stepper.step_body_plane(model, data, -1, s["dt"], None, None, thr, substeps=K, count=True, arith="strict")
+                res[compact] = state_of(data) + tuple(c.copy() for c in data.counters())
+            finally:
+                rb._lib.set_option("strict_compact", old)
+        for c in (4, 5):
+            for a, b in zip(res[0], res[c]):
+                assert np.array_equal(a, b), (kind, E, dtype, c)
+        assert res[4][2].sum() > E // 4                        # the horizon does exercise contacts
+        if dtype == np.float64 and kind == "sphere" and E > 1000:
+            qp, qv = s["qpos"].copy(), s["qvel"].copy()
+            cnt = (np.zeros(E, np.uint32), np.zeros(E, np.uint32))
+            model = build()
+            co.step_body_plane(qp, qv, 128, geom="sphere", mass=model.body_mass[-1], inertia=model.body_inertia[-1], size=0.2,
+                               plane_pos=[0, 0, 0], plane_normal=model.plane_normal, gravity=G, dt=s["dt"], restitution=e, friction=mu,
+                               threshold=0.0, counters=cnt)
+            assert np.array_equal(res[4][0], qp) and np.array_equal(res[4][1], qv)
+            assert np.array_equal(res[4][2][:, 0], cnt[0]) and np.array_equal(res[4][3][:, 0], cnt[1])
+
+
 def test_two_ball_golden_and_script(rb, golden):
     from rigidbody_simulation_b200.src.simulation import ball_collision
     s = golden("script_ball_collision_500")
