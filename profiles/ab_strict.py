@@ -28,7 +28,7 @@ for name in ("sphere_incline", "cube_bounce", "cube_incline"):
         kw = dict(restitution=0.2, friction_coeff=0.6, contact_threshold=1e-4)
     data = rb.BatchedData(model)
     ref = None
-    for compact, minb in ((0, 2), (0, 4), (0, 5), (4, 0), (5, 0)):
+    for compact, minb in ((-1, 2), (-1, 4), (-1, 5), (4, 0), (5, 0), (6, 0), (8, 0)):
         rb._lib.set_option("strict_compact", compact)
         rb._lib.set_option("strict_minb", minb)
         best = None
@@ -51,7 +51,7 @@ for name in ("sphere_incline", "cube_bounce", "cube_incline"):
             same = bool(torch.equal(ref, data.state))
         print(json.dumps({"config": name, "strict_compact": compact, "strict_minb": minb, "launch_ms": [round(m, 3) for m in best],
                           "env_substeps_per_s": E * K * L / (sum(best) * 1e-3), "state_bitwise_equal_to_first_variant": same}), flush=True)
-rb._lib.set_option("strict_compact", 4)
+rb._lib.set_option("strict_compact", 0)
 rb._lib.set_option("strict_minb", 0)
 
 # strict two-ball (config 3) and strict multi-sphere (config 5, 8,192 envs) ----------------------------------------------

@@ -50,7 +50,7 @@ Option g_options[] = {
     {"pf_min_substeps", "RBS_PF_MIN_SUBSTEPS", {0}, 4},      // shortest launch that takes the plane-frame kernels
     {"pf_packed", "RBS_PF_PACKED", {0}, 1},                  // float sphere stepper: packed fp32x2 kernel (1) or scalar (0)
     {"strict_minb", "RBS_STRICT_MINB", {0}, 0},              // resident CTAs per SM of the strict literal-inertia stepper (2, 4, 5, 6; 0 = tuned)
-    {"strict_compact", "RBS_STRICT_COMPACT", {0}, 4},        // strict single-body stepper: 0 = thread per environment, 4 / 5 = CTA-compacted contact path at 4 / 5 resident CTAs
+    {"strict_compact", "RBS_STRICT_COMPACT", {0}, 0},        // strict single-body stepper: -1 = thread per environment, 4 / 5 = CTA-compacted contact path, 0 = tuned
     {"strict_tb_minb", "RBS_STRICT_TB_MINB", {0}, 0},        // resident CTAs per SM of the strict two-ball stepper (3, 4, 5; 0 = tuned)
     {"strict_ms_regs", "RBS_STRICT_MS_REGS", {0}, 0},        // register cap of the strict literal-inertia multi-sphere stepper (168, 128, 96; 0 = tuned)
     {"box_minb", "RBS_BOX_MINB", {0}, 6},                    // resident CTAs per SM of the plane-frame box kernel
@@ -209,8 +209,19 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
         if constexpr (SCHEME == 0) {
             // the contact path compacted across the CTA (bit-identical results; strict_compact = 0 keeps one environment's
             // whole substep in its own thread).  Not with an applied wrench: then every lane builds the inverse anyway.
-            if (!a->xfrc && option("strict_compact") != 0) {
-                if (option("strict_compact") >= 5) {
+            // Option strict_compact: -1 = never, 4 / 5 = always (at 4 / 5 resident CTAs per SM), 0 = where it measured faster
+            // (profiles/r2_ab_strict.jsonl: sphere 2.28e10 -> 2.56e10 at 5 CTAs; cube 1.02e10 -> 7.7e9, so not for boxes: with
+            // only the hit environments' warps in the ~890-instruction dependent chain, the path turns latency-bound).
+            long compact = option("strict_compact");
+            if (compact == 0) compact = GEOM == 0 ? 5 : -1;
+            if (!a->xfrc && compact > 0) {
+                if (compact >= 8) {
+                    cudaFuncSetAttribute(rbs::step_body_plane_compact_kernel<T, GEOM, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                    rbs::step_body_plane_compact_kernel<T, GEOM, 8><<<grid, rbs::kBlock, 0, st>>>(p);
+                } else if (compact >= 6) {
+                    cudaFuncSetAttribute(rbs::step_body_plane_compact_kernel<T, GEOM, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                    rbs::step_body_plane_compact_kernel<T, GEOM, 6><<<grid, rbs::kBlock, 0, st>>>(p);
+                } else if (compact >= 5) {
                     cudaFuncSetAttribute(rbs::step_body_plane_compact_kernel<T, GEOM, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
                     rbs::step_body_plane_compact_kernel<T, GEOM, 5><<<grid, rbs::kBlock, 0, st>>>(p);
                 } else {
