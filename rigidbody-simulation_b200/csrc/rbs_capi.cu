@@ -269,9 +269,9 @@ template <typename T> void launch_sphere_plane_fast(const rbs_body_plane_args *a
                 return;
             }
         }
-        const bool wide = tuning_minb(a->substeps, RBS_ARITH_FAST) == 8;
+        const int pf_minb = tuning_minb(a->substeps, RBS_ARITH_FAST);
 #define RBS_PF(MINB, COUNT, THR) rbs::step_sphere_plane_pf_kernel<T, MINB, COUNT, THR><<<grid, rbs::kBlock, 0, st>>>(p)
-#define RBS_PF_MINB(COUNT, THR) do { if (wide) RBS_PF(8, COUNT, THR); else RBS_PF(6, COUNT, THR); } while (0)
+#define RBS_PF_MINB(COUNT, THR) do { if (pf_minb == 8) RBS_PF(8, COUNT, THR); else if (pf_minb == 7) RBS_PF(7, COUNT, THR); else if (pf_minb == 5) RBS_PF(5, COUNT, THR); else RBS_PF(6, COUNT, THR); } while (0)
         if (count) { if (thr) RBS_PF_MINB(true, true); else RBS_PF_MINB(true, false); }
         else { if (thr) RBS_PF_MINB(false, true); else RBS_PF_MINB(false, false); }
 #undef RBS_PF_MINB
