@@ -457,9 +457,22 @@ def b200_arm(args):
             "traffic": fig.get("dram_bytes_per_advance") if w.E == CONFIGS[name]["envs"] else None}
         if name == "multi_sphere64":
             out["body_substeps_per_s"] = out["value"] * 64
-            out["roofline"]["note"] = ("flops use SURVEY 8(d)'s all-pairs accounting (63 pair rejects per body-substep); the partner "
-                                       "lists skip most of those tests, so frac is throughput in the reference algorithm's units -- "
-                                       "pipe_fp64_active_pct is the hardware view")
+            if args.arith == "fast" and fig.get("issue_active_pct") is not None:
+                # The plane-frame multi-sphere kernel is bound by INSTRUCTION ISSUE (integer / FP32 partner-list work; FP64
+                # pipe ~13 % busy), so the fraction that means something is the issue-slot utilisation of the committed ncu
+                # capture.  The algorithmic-flop view (SURVEY 8(d)'s all-pairs accounting: 63 pair rejects per body-substep,
+                # most of which the lists never execute) is kept alongside and can exceed 1 for that reason.
+                r = out["roofline"]
+                out["roofline"] = {"bound": "issue", "kernel": r["kernel"], "achieved": fig["issue_active_pct"], "peak": 100.0,
+                                   "unit": "% of issue slots (ncu, profiles/ncu_figures.json)", "frac": fig["issue_active_pct"] / 100.0,
+                                   "pipe_fp64_active_pct": r["pipe_fp64_active_pct"], "ncu_source": r["ncu_source"], "traffic": r["traffic"],
+                                   "launch_ms": r["launch_ms"], "substeps_per_launch": r["substeps_per_launch"],
+                                   "contacts_per_env_substep": r["contacts_per_env_substep"], "impulses_per_env_substep": r["impulses_per_env_substep"],
+                                   "contacts_per_env_substep_next_horizon": r["contacts_per_env_substep_next_horizon"],
+                                   "impulses_per_env_substep_next_horizon": r["impulses_per_env_substep_next_horizon"],
+                                   "algorithmic_flops_view": {"achieved_TFLOPs": r["achieved"], "peak_TFLOPs": r["peak"], "frac": r["frac"],
+                                                              "frac_of_nominal": r["frac_of_nominal"], "flops_per_env_substep": r["flops_per_env_substep"],
+                                                              "note": "SURVEY 8(d) all-pairs accounting; the partner lists skip most of those tests"}}
         # the bit-faithful policy on the same job (exact contact-event counts by construction, profiles/r2_parity_report.md)
         other = "strict" if args.arith == "fast" else "fast"
         o_ms, _, _ = timed(lambda: w.step(arith=other), 1 if not headline else max(2, steps // 3), 1, before=w.reset)

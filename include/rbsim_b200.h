@@ -58,7 +58,7 @@ RBS_API int rbs_device_count(void);
 /* Tuning knobs of the launch dispatch (new; the reference has nothing to tune).  None changes what is computed, only
  * which kernel instantiation / launch shape computes it.  Every knob starts from the environment variable of the
  * same name in upper case with an RBS_ prefix (RBS_PF_MIN_SUBSTEPS ...).  Names: "minb", "pf_min_substeps",
- * "pf_packed", "strict_minb", "strict_compact", "strict_tb_minb", "strict_ms_regs", "box_minb", "box_compact", "tb_minb", "ms_skin_percent", "ms_kernel", "ms_walk_cost", "probe_mode", "host_chunks".
+ * "pf_packed", "strict_minb", "strict_compact", "strict_tb_minb", "strict_ms_regs", "box_minb", "box_compact", "tb_minb", "ms_skin_percent", "ms_kernel", "ms_walk_cost", "ms_tight_span", "ms_regs", "probe_mode", "host_chunks".
  * rbs_set_option returns RBS_EINVAL for an unknown name; rbs_get_option returns LONG_MIN for one. */
 RBS_API int rbs_set_option(const char *name, long value);
 RBS_API long rbs_get_option(const char *name);

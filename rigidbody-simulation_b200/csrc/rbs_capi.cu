@@ -59,6 +59,8 @@ Option g_options[] = {
     {"ms_skin_percent", "RBS_MS_SKIN_PERCENT", {0}, 50},     // starting skin of the adaptive partner lists
     {"ms_kernel", "RBS_MS_KERNEL", {0}, 2},                  // multi-sphere fast policy: 2 = plane-frame kernel, 1 = first generation
     {"ms_walk_cost", "RBS_MS_WALK_COST", {0}, 40},           // plane-frame multi-sphere kernel: cost of a list entry per substep (skin controller)
+    {"ms_tight_span", "RBS_MS_TIGHT_SPAN", {0}, 32},         // plane-frame multi-sphere kernel: substeps per TIGHT (no-skin) span, 0 = never
+    {"ms_regs", "RBS_MS_REGS", {0}, 96},                     // register cap of the frictionless plane-frame multi-sphere kernel (96 or 128)
     {"probe_mode", "RBS_PROBE_MODE", {0}, 1},                // rbs_fma_probe operand mode
     {"host_chunks", "RBS_HOST_CHUNKS", {0}, 16},             // pipeline depth of rbs_run_body_plane_host
 };
@@ -431,6 +433,7 @@ template <typename T> rbs::MultiSphereParams<T> make_params(const rbs_multi_sphe
     p.skin = skin_pct > 0 ? (T)(skin_pct * 0.01) : T(0);
     p.skin_adapt = a->list_skin_percent == 0 && skin_pct > 0;
     p.walk_cost = (int)option("ms_walk_cost");
+    p.tight_span = (int)option("ms_tight_span");
     {
         double R[9], q[4], gpf[3];
         plane_frame(a->plane_normal, a->gravity, a->dt, R, q, gpf);
@@ -510,7 +513,11 @@ template <typename T> int launch_multi_sphere(const rbs_multi_sphere_args *a, co
         KERNEL<<<grid, threads, smem_pf, st>>>(p);                                                              \
     } while (0)
         const bool mu0 = a->friction == 0.0;
-        if (threads <= 256) { if (mu0) RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 256, true>)); else RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 256, false>)); }
+        if (threads <= 256) {
+            if (mu0 && option("ms_regs") >= 128) RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 256, true, 128>));
+            else if (mu0) RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 256, true>));
+            else RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 256, false>));
+        }
         else if (threads <= 512) { if (mu0) RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 512, true>)); else RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 512, false>)); }
         else { if (mu0) RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 1024, true>)); else RBS_MS_LAUNCH_PF((rbs::step_multi_sphere_pf_kernel<T, 1024, false>)); }
 #undef RBS_MS_LAUNCH_PF

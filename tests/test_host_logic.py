@@ -380,7 +380,7 @@ def test_tuning_options_api():
     assert lib.get_option("pf_min_substeps") == 1
     lib.set_option("pf_min_substeps", old)
     assert lib.get_option("pf_min_substeps") == old
-    for name in ("minb", "pf_packed", "strict_minb", "strict_compact", "strict_tb_minb", "strict_ms_regs", "box_minb", "box_compact", "tb_minb", "ms_skin_percent", "ms_kernel", "ms_walk_cost", "probe_mode", "host_chunks"):
+    for name in ("minb", "pf_packed", "strict_minb", "strict_compact", "strict_tb_minb", "strict_ms_regs", "box_minb", "box_compact", "tb_minb", "ms_skin_percent", "ms_kernel", "ms_walk_cost", "ms_tight_span", "ms_regs", "probe_mode", "host_chunks"):
         lib.get_option(name)
     with pytest.raises(ValueError):
         lib.get_option("no_such_knob")
