@@ -1,4 +1,5 @@
-"""A/B of the two-ball fast kernel's occupancy variants (option tb_minb = 5 / 6 / 8 resident CTAs per SM) on config 3
+"""A/B of the two-ball fast kernel's occupancy variants (option tb_minb = 5 / 6 / 8 resident CTAs per SM; tb_packed = the
+fp32x2 kernel with two envs per thread, float only) on config 3
 (1,048,576 envs), fp64 and fp32: 2048 substeps from the initial state in 8 launches of 256; one JSON line per run.
     python profiles/ab_two_ball.py
 """
@@ -20,8 +21,9 @@ s = synth.two_ball(E)
 for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
     model, data = ball_collision.build(E, device=dev, dtype=dtype)
     ref = None
-    for minb in (5, 6, 8):
+    for minb, packed in ((5, 0), (6, 0), (8, 0)) + (((4, 1), (6, 1), (8, 1)) if tag == "fp32" else ()):
         rb._lib.set_option("tb_minb", minb)
+        rb._lib.set_option("tb_packed", packed)
         best = None
         for rep in range(3):
             data.set_state(s["qpos"], s["qvel"])
@@ -39,6 +41,7 @@ for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
             ref = data.state.clone()
         else:
             same = bool(torch.equal(ref, data.state))
-        print(json.dumps({"dtype": tag, "tb_minb": minb, "launch_ms": [round(m, 3) for m in best],
+        print(json.dumps({"dtype": tag, "tb_minb": minb, "tb_packed": packed, "launch_ms": [round(m, 3) for m in best],
                           "env_substeps_per_s_2048": E * K * L / (sum(best) * 1e-3), "state_bitwise_equal_to_first_variant": same}), flush=True)
 rb._lib.set_option("tb_minb", 0)
+rb._lib.set_option("tb_packed", 0)

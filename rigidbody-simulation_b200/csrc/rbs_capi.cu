@@ -56,6 +56,7 @@ Option g_options[] = {
     {"box_minb", "RBS_BOX_MINB", {0}, 6},                    // resident CTAs per SM of the plane-frame box kernel
     {"box_compact", "RBS_BOX_COMPACT", {0}, 0},              // plane-frame box kernel: CTA-level compaction of contacts (measured slower: off)
     {"tb_minb", "RBS_TB_MINB", {0}, 0},                      // resident CTAs per SM of the two-ball fast kernel (5, 6 or 8; 0 = 6 in double, 8 in float)
+    {"tb_packed", "RBS_TB_PACKED", {0}, 0},                  // float two-ball fast stepper: packed fp32x2 kernel, two envs per thread (1) or scalar (0: measured equal, fewer ragged waves)
     {"ms_skin_percent", "RBS_MS_SKIN_PERCENT", {0}, 50},     // starting skin of the adaptive partner lists
     {"ms_kernel", "RBS_MS_KERNEL", {0}, 2},                  // multi-sphere fast policy: 2 = plane-frame kernel, 1 = first generation
     {"ms_walk_cost", "RBS_MS_WALK_COST", {0}, 40},           // plane-frame multi-sphere kernel: cost of a list entry per substep (skin controller)
@@ -564,8 +565,21 @@ int launch_two_ball_any(const rbs_two_ball_args *a, const Window &w) {
         rbs::step_two_ball_fast_kernel<T, GZ, MINB><<<grid, rbs::kBlock, 0, st>>>(make_params<T>(a, w));                    \
     } while (0)
 #define RBS_TB_MINB(T, GZ) do { if (minb >= 8) RBS_TB(T, GZ, 8); else if (minb >= 6) RBS_TB(T, GZ, 6); else RBS_TB(T, GZ, 5); } while (0)
+#define RBS_TB2(GZ, MINB)                                                                                                \
+    do {                                                                                                                 \
+        cudaFuncSetAttribute(rbs::step_two_ball_fast2_kernel<GZ, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,    \
+                             cudaSharedmemCarveoutMaxShared);                                                            \
+        rbs::step_two_ball_fast2_kernel<GZ, MINB><<<blocks_for(w.cnt, 2 * rbs::kBlock), rbs::kBlock, 0, st>>>(make_params<float>(a, w)); \
+    } while (0)
+#define RBS_TB2_MINB(GZ) do { if (minb >= 8) RBS_TB2(GZ, 8); else if (minb >= 6) RBS_TB2(GZ, 6); else RBS_TB2(GZ, 4); } while (0)
         if (a->dtype == RBS_F64) { if (gz) RBS_TB_MINB(double, true); else RBS_TB_MINB(double, false); }
+        else if (option("tb_packed") != 0) {   // two environments per thread on packed fp32x2 instructions (same bits as the scalar kernel)
+            if (option("tb_minb") == 0) minb = 6;
+            if (gz) RBS_TB2_MINB(true); else RBS_TB2_MINB(false);
+        }
         else { if (gz) RBS_TB_MINB(float, true); else RBS_TB_MINB(float, false); }
+#undef RBS_TB2_MINB
+#undef RBS_TB2
 #undef RBS_TB_MINB
 #undef RBS_TB
     } else {

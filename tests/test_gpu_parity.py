@@ -1323,6 +1323,36 @@ def test_packed_float_kernel_matches_scalar_kernel(rb):
             assert res["1"][2].sum() > E // 2                      # the horizon does exercise contacts
 
 
+def test_packed_float_two_ball_kernel_matches_scalar_kernel(rb):
+    """Float launches of the two-ball fast stepper run two environments per thread on packed fp32x2 instructions
+    (step_two_ball_fast2_kernel); the rare event paths are the scalar kernel's statements on the unpacked slot, so state
+    and both event counters must be the scalar kernel's numbers bit for bit (option tb_packed=0 selects it): ragged sizes
+    (odd, smaller than one CTA, a tail of less than one CTA in the second slot), shipped and tilted gravity (the GZ and the
+    general instantiation), over a horizon with ground hits and pair hits.  The bar against the oracle for the float
+    kernel is test_two_ball_fast_policy_vs_oracle[float32], whose launches take this path by default."""
+    from rigidbody_simulation_b200 import stepper, synth
+    from rigidbody_simulation_b200.src.simulation import ball_collision
+    dev = torch.device("cuda:0")
+    for E, grav in ((100_003, None), (77, None), (65_536 + 129, (0.3, -0.2, -9.8)), (256, None)):
+        s = synth.two_ball(E)
+        res = {}
+        for packed in (0, 1):
+            old = rb._lib.set_option("tb_packed", packed)
+            try:
+                model, data = ball_collision.build(E, device=dev, dtype=torch.float32)
+                if grav is not None:
+                    model.opt.gravity[:] = grav
+                data.set_state(s["qpos"], s["qvel"])
+                for K in (4, 260, 37, 1, 150):
+                    stepper.step_two_ball(model, data, 0.01, 1.0, 0.3, radius=0.1, substeps=K, count=True, arith="fast")
+                res[packed] = state_of(data) + tuple(c.copy() for c in data.counters())
+            finally:
+                rb._lib.set_option("tb_packed", old)
+        for a, b in zip(res[0], res[1]):
+            assert np.array_equal(a, b), (E, grav, np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max())
+        assert res[1][2].sum() > E // 2 and res[1][3].sum() > E // 4    # ground hits and pair hits both happen
+
+
 def test_two_ball_tilted_gravity_both_policies(rb):
     """The two-ball fast kernel has a gravity-along-z instantiation (every shipped model) and a general one: a gravity
     vector with horizontal components goes through the general one and must meet the same bar against the oracle;
