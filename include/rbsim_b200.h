@@ -198,6 +198,41 @@ typedef struct rbs_multi_sphere_args {
 RBS_API int rbs_step_multi_sphere(const rbs_multi_sphere_args *a);
 
 /* ---------------------------------------------------------------------------------------------
+ * SURVEY.md section 8(f) row N4 -- multi-body scenes with spheres AND boxes (new behaviour: the reference's scripts
+ * only ever meet plane-sphere, plane-box and sphere-sphere contacts).  The step is the loop rbs_step_multi_sphere
+ * replaces (src/simulation/multi_sphere_bounce.py:42-92, repaired), body by body with the reference's impulse
+ * (src/physics/collision.py:7-48), its application (src/physics/physics_utils.py:25-49) and the literal world inertia
+ * (collision.py:51-53) per contact, strict arithmetic; the contact set adds sphere-box and box-box (vertex-face)
+ * pairs, geom1 = the lower body index, normal geom1 -> geom2, never flipped (DESIGN.md "N4").
+ * body_table: DEVICE array [n_body][RBS_BODY_TABLE_WIDTH] of dtype, shared by every environment; per body
+ *   [0] geom type (0 sphere, 1 box)   [1..3] size (radius,-,- | half extents)   [4] mass   [5..7] principal inertia
+ *   [8..10] geom position and [11..14] geom quaternion (wxyz) in the body frame (read only when has_offset != 0)
+ *   [15] radius of the geom's bounding sphere times (1 + 1e-6) (broad phase).
+ * State layout: body-fastest, as rbs_step_multi_sphere.
+ * --------------------------------------------------------------------------------------------- */
+#define RBS_BODY_TABLE_WIDTH 16
+typedef struct rbs_multi_body_args {
+    int dtype;
+    int substeps;
+    int n_body;                /* 1 .. 256 */
+    int has_offset;            /* 0: every geom sits at its body's origin with the body's orientation */
+    long n_env;
+    long stride;               /* >= n_env * n_body */
+    void *state;               /* [13][stride], body-fastest */
+    const void *body_table;    /* [n_body][RBS_BODY_TABLE_WIDTH] */
+    double plane_point[3];
+    double plane_normal[3];
+    double gravity[3];
+    double dt;
+    double restitution;
+    double friction;
+    unsigned *n_contacts;      /* [n_env * n_body] or NULL */
+    unsigned *n_impulses;      /* [n_env * n_body] or NULL */
+    void *stream;
+} rbs_multi_body_args;
+RBS_API int rbs_step_multi_body(const rbs_multi_body_args *a);
+
+/* ---------------------------------------------------------------------------------------------
  * Layout conversion between the reference's per-env qpos[7*B] / qvel[6*B] and the SoA state.
  * body_fastest = 0 -> env-major layout, 1 -> body-fastest layout (see top of file).
  * --------------------------------------------------------------------------------------------- */

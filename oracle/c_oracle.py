@@ -152,6 +152,30 @@ def step_multi_sphere(qpos, qvel, steps, *, mass, inertia, radius, plane_pos, pl
         creal(dt), creal(restitution), creal(friction), _p(calls), _p(imps))
 
 
+def step_multi_body(qpos, qvel, steps, *, gtype, mass, inertia, size, plane_pos, plane_normal, gravity, dt, restitution,
+                    friction, geom_pos=None, geom_quat=None, counters=None):
+    """N4: the repaired A9 loop for E envs of B bodies, each a sphere (gtype 0, size[0] = radius) or a box (gtype 1, half
+    extents); gtype[B], mass[B], inertia[B,3], size[B,3], geom_pos[B,3] / geom_quat[B,4] (or None) are shared by all
+    environments.  qpos[E,B,7], qvel[E,B,6] in place."""
+    dtype = qpos.dtype
+    suf, creal = _suffix(dtype)
+    assert qpos.flags.c_contiguous and qvel.flags.c_contiguous
+    E, B = qpos.shape[0], qpos.shape[1]
+    calls, imps = counters if counters is not None else (None, None)
+    gt = np.ascontiguousarray(gtype, dtype=np.int32)
+    assert gt.shape == (B,)
+    gp = None if geom_pos is None else _arr(geom_pos, dtype, (B, 3))
+    gq = None if geom_quat is None else _arr(geom_quat, dtype, (B, 4))
+    if (gp is None) != (gq is None):
+        gp = _arr(np.zeros((B, 3)), dtype) if gp is None else gp
+        gq = _arr(np.tile([1.0, 0, 0, 0], (B, 1)), dtype) if gq is None else gq
+    getattr(lib(), "rbo_step_multi_body" + suf)(
+        ctypes.c_long(E), ctypes.c_int(B), ctypes.c_int(int(steps)), _p(qpos), _p(qvel), _p(gt),
+        _p(_arr(mass, dtype, (B,))), _p(_arr(inertia, dtype, (B, 3))), _p(_arr(size, dtype, (B, 3))), _p(gp), _p(gq),
+        _p(_arr(plane_pos, dtype, (3,))), _p(_arr(plane_normal, dtype, (3,))), _p(_arr(gravity, dtype, (3,))),
+        creal(dt), creal(restitution), creal(friction), _p(calls), _p(imps))
+
+
 def step_two_ball(qpos, qvel, steps, *, mass, radius, gravity, dt, restitution, friction, counters=None):
     """A11 for E two-ball envs.  qpos[E,14], qvel[E,12] in place; counters = (ground_hits[E], pair_hits[E])."""
     dtype = qpos.dtype

@@ -344,6 +344,185 @@ void SUF(rbo_step_multi_sphere)(long E, int B, int steps, REAL *qpos, REAL *qvel
     }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * N4: multi-body scenes with spheres AND boxes.  NOT in the reference (its scripts only ever
+ * meet plane-sphere, plane-box and sphere-sphere): the STEP is the repaired A9 loop above, body by body, with the
+ * reference's A1 / A2 / A4 per contact; the CONTACT SET is widened by the two pair functions below, which are this
+ * project's own specification (DESIGN.md "N4"), written in the conventions of Appendix A.2 -- contact = {dist, pos midway
+ * between the two surfaces, normal from geom1 to geom2}.  Parity of these two against MuJoCo's mjc_SphereBox /
+ * mjc_BoxBox is NOT claimed (box-box here has vertex-face contacts only, no edge-edge).
+ * Geoms may sit at an offset in their body's frame (gpos, gquat: N1 remainder); the impulse arm is still taken from the
+ * body origin qpos[:3], as the reference does (collision.py:75).
+ * ------------------------------------------------------------------------------------------------ */
+static void SUF(plane_box_rot)(const REAL *pp, const REAL *n, const REAL *c, const REAL *R, const REAL *half,
+                               SUF(contact_t) *out, int *count) {
+    REAL d[3] = {c[0] - pp[0], c[1] - pp[1], c[2] - pp[2]};
+    REAL d0 = V3DOT(d, n);
+    int cnt = 0;
+    for (int i = 0; i < 8 && cnt < 4; ++i) {
+        REAL v[3] = {(i & 1) ? half[0] : -half[0], (i & 2) ? half[1] : -half[1], (i & 4) ? half[2] : -half[2]};
+        REAL corner[3];
+        SUF(matvec3)(R, v, corner);
+        REAL ld = V3DOT(n, corner);
+        if (d0 + ld > 0 || ld > 0) continue;
+        REAL dist = d0 + ld;
+        REAL hs = (REAL)0.5 * dist;
+        for (int k = 0; k < 3; ++k) { out[cnt].pos[k] = (c[k] + corner[k]) - n[k] * hs; out[cnt].n[k] = n[k]; }
+        out[cnt].dist = dist;
+        ++cnt;
+    }
+    *count = cnt;
+}
+
+/* x in the frame of a box at c with rotation R (columns = box axes): R^T (x - c) */
+static void SUF(to_box_frame)(const REAL *c, const REAL *R, const REAL *x, REAL *o) {
+    REAL d[3] = {x[0] - c[0], x[1] - c[1], x[2] - c[2]};
+    for (int k = 0; k < 3; ++k) o[k] = (R[k] * d[0] + R[3 + k] * d[1]) + R[6 + k] * d[2];
+}
+
+/* sphere - box.  The closest point of the box to the sphere centre is the centre clamped to the box in the box frame; a
+ * centre inside the box leaves through the nearest face.  geom1 is the body with the LOWER INDEX, as for sphere pairs
+ * (MuJoCo itself would put the lower geom TYPE first; with the A9 loop's never-flipped normal that would make every
+ * sphere blind to every box, so the index rule is kept for all pair types): sign = +1 when the sphere is geom1 (normal
+ * sphere -> box), -1 when the box is. */
+static int SUF(sphere_box)(const REAL *cs, REAL rad, const REAL *cb, const REAL *Rb, const REAL *h, REAL sign,
+                           SUF(contact_t) *out) {
+    REAL c[3], cl[3], e[3], nl[3], pl[3], dist;
+    SUF(to_box_frame)(cb, Rb, cs, c);
+    for (int k = 0; k < 3; ++k) { cl[k] = c[k] < -h[k] ? -h[k] : (c[k] > h[k] ? h[k] : c[k]); e[k] = cl[k] - c[k]; }
+    REAL L = SUF(sqrtr)((e[0] * e[0] + e[1] * e[1]) + e[2] * e[2]);
+    if (L >= (REAL)1e-15) {
+        dist = L - rad;
+        if (dist > 0) return 0;
+        REAL s = rad + (REAL)0.5 * dist;
+        for (int k = 0; k < 3; ++k) { nl[k] = e[k] / L; pl[k] = c[k] + nl[k] * s; }
+    } else {
+        int ax = 0;
+        REAL depth = h[0] - SUF(absr)(c[0]);
+        for (int k = 1; k < 3; ++k) { REAL dk = h[k] - SUF(absr)(c[k]); if (dk < depth) { depth = dk; ax = k; } }
+        dist = -(rad + depth);
+        REAL s = (REAL)0.5 * (rad - depth);
+        for (int k = 0; k < 3; ++k) { nl[k] = 0; pl[k] = c[k]; }
+        nl[ax] = c[ax] >= 0 ? (REAL)-1 : (REAL)1;
+        pl[ax] = c[ax] + nl[ax] * s;
+    }
+    REAL nw[3], pw[3];
+    SUF(matvec3)(Rb, nl, nw);
+    SUF(matvec3)(Rb, pl, pw);
+    for (int k = 0; k < 3; ++k) { out->n[k] = sign * nw[k]; out->pos[k] = cb[k] + pw[k]; }
+    out->dist = dist;
+    return 1;
+}
+
+/* vertices of box V (centre cv, rotation Rv, half extents hv; index order, bit0->x bit1->y bit2->z) that lie inside box F:
+ * each leaves F through its nearest face.  sign = +1 when F is geom1 (the face normal already points geom1 -> geom2),
+ * -1 when F is geom2.  Appends to out[], at most `room` contacts. */
+static int SUF(box_vertices_in_box)(const REAL *cv, const REAL *Rv, const REAL *hv, const REAL *cf, const REAL *Rf,
+                                    const REAL *hf, REAL sign, SUF(contact_t) *out, int room) {
+    int cnt = 0;
+    for (int i = 0; i < 8 && cnt < room; ++i) {
+        REAL v[3] = {(i & 1) ? hv[0] : -hv[0], (i & 2) ? hv[1] : -hv[1], (i & 4) ? hv[2] : -hv[2]};
+        REAL corner[3], x[3], l[3];
+        SUF(matvec3)(Rv, v, corner);
+        for (int k = 0; k < 3; ++k) x[k] = cv[k] + corner[k];
+        SUF(to_box_frame)(cf, Rf, x, l);
+        int ax = 0;
+        REAL depth = hf[0] - SUF(absr)(l[0]);
+        for (int k = 1; k < 3; ++k) { REAL dk = hf[k] - SUF(absr)(l[k]); if (dk < depth) { depth = dk; ax = k; } }
+        if (!(depth > 0)) continue;                       /* outside F (or on its surface) */
+        REAL sg = l[ax] >= 0 ? (REAL)1 : (REAL)-1;        /* outward normal of the nearest face: sg * axis ax of F */
+        REAL m[3] = {sg * Rf[ax], sg * Rf[3 + ax], sg * Rf[6 + ax]};
+        REAL hd = (REAL)0.5 * depth;
+        for (int k = 0; k < 3; ++k) { out[cnt].pos[k] = x[k] + m[k] * hd; out[cnt].n[k] = sign * m[k]; }
+        out[cnt].dist = -depth;
+        ++cnt;
+    }
+    return cnt;
+}
+
+/* box (geom1 = lower id) - box (geom2): vertices of geom2 inside geom1, then vertices of geom1 inside geom2; <= 8 */
+static int SUF(box_box)(const REAL *c1, const REAL *R1, const REAL *h1, const REAL *c2, const REAL *R2, const REAL *h2,
+                        SUF(contact_t) *out) {
+    int cnt = SUF(box_vertices_in_box)(c2, R2, h2, c1, R1, h1, (REAL)1, out, 8);
+    cnt += SUF(box_vertices_in_box)(c1, R1, h1, c2, R2, h2, (REAL)-1, out + cnt, 8 - cnt);
+    return cnt;
+}
+
+/* world pose of a body's geom: centre and rotation matrix (mju_quat2Mat of the normalised quaternion) */
+static void SUF(geom_pose)(const REAL *p, const REAL *q, int has_off, const REAL *gpos, const REAL *gquat, REAL *c, REAL *R) {
+    if (!has_off) {
+        for (int k = 0; k < 3; ++k) c[k] = p[k];
+        SUF(rot_mujoco)(q, R);
+        return;
+    }
+    REAL Rb[9], off[3], qq[4];
+    SUF(rot_mujoco)(q, Rb);
+    SUF(matvec3)(Rb, gpos, off);
+    for (int k = 0; k < 3; ++k) c[k] = p[k] + off[k];
+    SUF(mulquat)(q, gquat, qq);
+    SUF(rot_mujoco)(qq, R);
+}
+
+/* gtype[B]: 0 sphere (size[0] = radius), 1 box (size = half extents); mass[B], inertia3[B][3], size3[B][3] and the geom
+ * offsets gpos3[B][3] / gquat4[B][4] (NULL = none) describe ONE environment's bodies and are shared by all E.
+ * Layout: qpos[E][B][7], qvel[E][B][6]; counters per body [E][B]. */
+void SUF(rbo_step_multi_body)(long E, int B, int steps, REAL *qpos, REAL *qvel, const int *gtype, const REAL *mass,
+                              const REAL *inertia3, const REAL *size3, const REAL *gpos3, const REAL *gquat4,
+                              const REAL *plane_pos3, const REAL *plane_normal3, const REAL *gravity3, REAL dt,
+                              REAL rest, REAL fric, unsigned *calls, unsigned *impulses) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (long e = 0; e < E; ++e) {
+        REAL *QP = qpos + (long)7 * B * e, *QV = qvel + (long)6 * B * e;
+        REAL *gc = (REAL *)malloc(sizeof(REAL) * 12 * B);            /* start-of-step geom centre [3] + rotation [9] */
+        for (int s = 0; s < steps; ++s) {
+            for (int b = 0; b < B; ++b)                              /* mj_forward once per step (:43) */
+                SUF(geom_pose)(QP + 7 * b, QP + 7 * b + 3, gpos3 != 0, gpos3 ? gpos3 + 3 * b : 0, gquat4 ? gquat4 + 4 * b : 0,
+                               gc + 12 * b, gc + 12 * b + 3);
+            for (int b = 0; b < B; ++b) {                            /* :46 */
+                long eb = e * B + b;
+                REAL *qp = QP + 7 * b, *qv = QV + 6 * b;
+                REAL Iw[9];
+                SUF(inertia_world_one)(inertia3 + 3 * b, qp + 3, Iw);              /* :55 */
+                REAL vel[3] = {qv[0], qv[1], qv[2]}, om[3] = {qv[3], qv[4], qv[5]};
+                SUF(external_forces)(vel, om, mass[b], Iw, gravity3, 0, dt);       /* :58-61 */
+                for (int j = -1; j < B; ++j) {                       /* :64, MuJoCo contact order for body b */
+                    SUF(contact_t) con[8];
+                    int ncon = 0;
+                    if (j == b) continue;
+                    const REAL *cb_ = gc + 12 * b, *Rb_ = cb_ + 3, *hb_ = size3 + 3 * b;
+                    if (j < 0) {
+                        if (gtype[b] == 0) ncon = SUF(plane_sphere)(plane_pos3, plane_normal3, cb_, hb_[0], con);
+                        else SUF(plane_box_rot)(plane_pos3, plane_normal3, cb_, Rb_, hb_, con, &ncon);
+                    } else {
+                        int lo = j < b ? j : b, hi = j < b ? b : j;
+                        const REAL *cl = gc + 12 * lo, *ch = gc + 12 * hi;
+                        const REAL *hl = size3 + 3 * lo, *hh = size3 + 3 * hi;
+                        if (gtype[lo] == 0 && gtype[hi] == 0) ncon = SUF(sphere_sphere)(cl, hl[0], ch, hh[0], con);
+                        else if (gtype[lo] == 1 && gtype[hi] == 1) ncon = SUF(box_box)(cl, cl + 3, hl, ch, ch + 3, hh, con);
+                        else if (gtype[lo] == 0) ncon = SUF(sphere_box)(cl, hl[0], ch, ch + 3, hh, (REAL)1, con);
+                        else ncon = SUF(sphere_box)(ch, hh[0], cl, cl + 3, hl, (REAL)-1, con);
+                    }
+                    for (int i = 0; i < ncon; ++i) {
+                        if (!(con[i].dist < 0)) continue;            /* :66 */
+                        REAL r[3] = {con[i].pos[0] - qp[0], con[i].pos[1] - qp[1], con[i].pos[2] - qp[2]};   /* :67 */
+                        REAL jn, jt[3];
+                        int imp = SUF(impulse_friction_one)(mass[b], vel, om, r, con[i].n, rest, fric, &jn, jt);   /* :69 */
+                        if (calls) calls[eb] += 1;
+                        if (impulses) impulses[eb] += (unsigned)imp;
+                        SUF(apply_impulse_friction_one)(vel, om, mass[b], Iw, r, con[i].n, jn, jt);                /* :72 */
+                    }
+                }
+                for (int i = 0; i < 3; ++i) qp[i] = qp[i] + vel[i] * dt;           /* :77 */
+                SUF(integrate_quat)(qp + 3, om, dt);                               /* :78-82 */
+                for (int i = 0; i < 3; ++i) { qv[i] = vel[i]; qv[3 + i] = om[i]; } /* :85-88 */
+            }
+        }
+        free(gc);
+    }
+}
+
 /* A10  compute_collision_impulse  src/simulation/ball_collision.py:53-68 (I_inv = iinv * Id, :39-41) */
 static void SUF(two_ball_impulse)(REAL mass, REAL iinv, const REAL *v, const REAL *w, const REAL *r, const REAL *n,
                                   REAL e, REAL mu, REAL *J) {

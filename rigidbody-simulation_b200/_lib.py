@@ -73,6 +73,21 @@ class MultiSphereArgs(Structure):
     ]
 
 
+class MultiBodyArgs(Structure):
+    """struct rbs_multi_body_args"""
+    _fields_ = [
+        ("dtype", c_int), ("substeps", c_int), ("n_body", c_int), ("has_offset", c_int),
+        ("n_env", c_long), ("stride", c_long),
+        ("state", c_void_p), ("body_table", c_void_p),
+        ("plane_point", D3), ("plane_normal", D3), ("gravity", D3),
+        ("dt", c_double), ("restitution", c_double), ("friction", c_double),
+        ("n_contacts", c_void_p), ("n_impulses", c_void_p),
+        ("stream", c_void_p),
+    ]
+
+
+RBS_BODY_TABLE_WIDTH = 16
+
 # name -> (restype, argtypes); this table is also what tests/test_cabi.py checks against the header
 PROTOTYPES = {
     "rbs_version": (c_int, []),
@@ -93,6 +108,7 @@ PROTOTYPES = {
     "rbs_step_body_plane": (c_int, [POINTER(BodyPlaneArgs)]),
     "rbs_step_two_ball": (c_int, [POINTER(TwoBallArgs)]),
     "rbs_step_multi_sphere": (c_int, [POINTER(MultiSphereArgs)]),
+    "rbs_step_multi_body": (c_int, [POINTER(MultiBodyArgs)]),
     "rbs_pack_state": (c_int, [c_int, c_long, c_int, c_int, c_void_p, c_void_p, c_void_p, c_long, c_void_p]),
     "rbs_unpack_state": (c_int, [c_int, c_long, c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p]),
     "rbs_reset_envs": (c_int, [c_int, c_long, c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

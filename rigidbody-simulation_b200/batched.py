@@ -59,6 +59,8 @@ class BatchedModel:
         else:
             self.plane_point, self.plane_normal = None, None
         self.body_geom = {i: scene.geoms[scene.bodies[i].geoms[0]] for i in self.free_ids}
+        # geoms placed off their body's origin / axes: only stepper.step_multi_body generates contacts for those
+        self.has_offset_geoms = any(any(g.pos) or list(g.quat) != [1.0, 0.0, 0.0, 0.0] for g in self.body_geom.values())
         self.per_env = {}
 
     # -- construction ------------------------------------------------------------------------------

@@ -549,6 +549,37 @@ template <typename T> int launch_multi_sphere(const rbs_multi_sphere_args *a, co
     return RBS_OK;
 }
 
+template <typename T> int launch_multi_body(const rbs_multi_body_args *a) {
+    rbs::MultiBodyParams<T> p;
+    const int B = a->n_body;
+    p.n_env = a->n_env;
+    p.stride = a->stride;
+    p.substeps = a->substeps;
+    p.n_body = B;
+    p.env_per_block = 256 / B;
+    p.has_offset = a->has_offset;
+    p.state = static_cast<T *>(a->state);
+    p.table = static_cast<const T *>(a->body_table);
+    for (int i = 0; i < 3; ++i) {
+        p.pp[i] = (T)a->plane_point[i];
+        p.pn[i] = (T)a->plane_normal[i];
+        p.g[i] = (T)a->gravity[i];
+    }
+    p.dt = (T)a->dt;
+    p.rest = (T)a->restitution;
+    p.fric = (T)a->friction;
+    p.n_contacts = a->n_contacts;
+    p.n_impulses = a->n_impulses;
+    const int threads = ((p.env_per_block * B + 31) / 32) * 32;
+    const size_t smem = ((size_t)B * rbs::kBodyTable + 2 * (size_t)p.env_per_block * B * 12) * sizeof(T);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(rbs::step_multi_body_kernel<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(RBS_ECUDA, "rbs_step_multi_body: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    }
+    rbs::step_multi_body_kernel<T, 256><<<blocks_for(a->n_env, p.env_per_block), threads, smem, as_stream(a->stream)>>>(p);
+    return check_launch("rbs_step_multi_body");
+}
+
 int launch_two_ball_any(const rbs_two_ball_args *a, const Window &w) {
     const unsigned grid = blocks_for(w.cnt, rbs::kBlock);
     cudaStream_t st = w.stream;
@@ -932,6 +963,20 @@ int rbs_step_multi_sphere(const rbs_multi_sphere_args *a) {
     if (rc) return rc;
     if (a->n_env == 0) return RBS_OK;
     return launch_multi_sphere_any(a, whole(a));
+}
+
+int rbs_step_multi_body(const rbs_multi_body_args *a) {
+    if (!a) return fail(RBS_EINVAL, "rbs_step_multi_body: null args");
+    if (bad_dtype(a->dtype)) return fail(RBS_EINVAL, "rbs_step_multi_body: dtype %d is not RBS_F32/RBS_F64", a->dtype);
+    if (a->n_body < 1 || a->n_body > 256) return fail(RBS_EINVAL, "rbs_step_multi_body: n_body %d outside 1..256", a->n_body);
+    if (a->n_env < 0) return fail(RBS_EINVAL, "rbs_step_multi_body: n_env %ld < 0", a->n_env);
+    if (a->substeps < 1) return fail(RBS_EINVAL, "rbs_step_multi_body: substeps %d < 1", a->substeps);
+    if (!a->body_table) return fail(RBS_EINVAL, "rbs_step_multi_body: null body_table");
+    if (a->n_env > 0 && !a->state) return fail(RBS_EINVAL, "rbs_step_multi_body: null state");
+    if (a->stride < a->n_env * a->n_body)
+        return fail(RBS_EINVAL, "rbs_step_multi_body: stride %ld < n_env*n_body %ld", a->stride, a->n_env * a->n_body);
+    if (a->n_env == 0) return RBS_OK;
+    return a->dtype == RBS_F64 ? launch_multi_body<double>(a) : launch_multi_body<float>(a);
 }
 
 int rbs_pack_state(int dtype, long n_env, int n_body, int body_fastest, const void *qpos, const void *qvel,

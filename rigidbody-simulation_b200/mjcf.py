@@ -14,8 +14,12 @@ document order; ``inertiafromgeom`` (true: always from the geoms, as in every re
 sphere m = rho*4/3*pi*r^3, I = 2/5 m r^2; box (half sizes a,b,c) m = 8*rho*a*b*c,
 I = m/3 * (b^2+c^2, a^2+c^2, a^2+b^2); top-level ``<default><geom .../></default>`` attributes.  solref / solimp /
 damping / friction attributes belong to MuJoCo's own solver, which the reference's path never runs, and are ignored.
+A geom may sit at an offset (pos / orientation) in its free body's frame: mass and principal moments are the geom's own
+(about its centre, as ``inertiafromgeom`` computes them), the reference's step keeps taking the impulse arm from the
+body origin qpos[:3] (collision.py:75), and only ``stepper.step_multi_body`` generates contacts for such a geom -- the
+single-body, two-ball and multi-sphere steppers raise ValueError (``BatchedModel.has_offset_geoms``).
 Outside the subset (rejected with ValueError, never approximated): other geom types, nested bodies, default classes,
-geoms or inertial frames offset from their free body's origin, several geoms on a free body.
+inertial frames offset from their free body's origin, several geoms on a free body.
 
 The reference templates ``{INCLINE_ANGLE}`` / ``{TIMESTEP}`` into the XML text before compiling
 (src/simulation/single_sphere_bounce.py:29-30, cube_incline.py:33-34); ``render_template`` does that.
@@ -272,8 +276,8 @@ def parse_string(text):
         for gel in el.findall("geom"):
             g = add_geom(gel, owner)
             m, inertia = geom_mass_inertia(g)
-            if free and m > 0.0 and (any(g.pos) or g.quat != [1.0, 0.0, 0.0, 0.0]):
-                raise ValueError("offset geoms on a free body are outside the supported subset")
+            # a geom offset from its free body's origin is kept (Geom.pos / Geom.quat in the body frame); only the
+            # multi-body stepper (stepper.step_multi_body) places geoms that way, the others refuse such a scene
             body.mass += m
             body.inertia = [a + b for a, b in zip(body.inertia, inertia)]
         if free and len(body.geoms) != 1:

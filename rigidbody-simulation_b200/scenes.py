@@ -36,6 +36,24 @@ def multi_sphere_xml(n_body, radius=0.1, timestep=0.01, gravity=(0.0, 0.0, -9.8)
             f'<geom name="ground" type="plane" size="5 5 0.1" euler="{fmt(plane_euler)}"/>{balls}</worldbody></mujoco>')
 
 
+def multi_body_xml(bodies, timestep=0.005, gravity=(0.0, 0.0, -9.8), density=50.0, plane_euler=(0.0, 0.0, 0.0)):
+    """A ground plane plus free bodies body1..bodyN for stepper.step_multi_body (N4).  ``bodies`` is a list of dicts:
+    {"type": "sphere" | "box", "size": [...], optional "pos" (body), "geom_pos", "geom_euler" (geom in the body frame)}."""
+    fmt = lambda v: " ".join(repr(float(x)) for x in v)
+    out = []
+    for i, b in enumerate(bodies):
+        off = ""
+        if "geom_pos" in b:
+            off += f' pos="{fmt(b["geom_pos"])}"'
+        if "geom_euler" in b:
+            off += f' euler="{fmt(b["geom_euler"])}"'
+        out.append(f'<body name="body{i + 1}" pos="{fmt(b.get("pos", (0, 0, 1 + i)))}"><joint name="joint{i + 1}" type="free"/>'
+                   f'<geom name="geom{i + 1}" type="{b["type"]}" size="{fmt(b["size"])}" density="{float(density)!r}"{off}/></body>')
+    return (f'<mujoco><compiler angle="radian" inertiafromgeom="true"/>'
+            f'<option gravity="{fmt(gravity)}" timestep="{float(timestep)!r}"/><worldbody>'
+            f'<geom name="ground" type="plane" size="5 5 0.1" euler="{fmt(plane_euler)}"/>{"".join(out)}</worldbody></mujoco>')
+
+
 def sphere_on_incline(nenv, theta=0.7, device=None, dtype=torch.float64):
     """config 2 scene: the sphere of models/sphere.xml over a plane tilted ``theta`` rad about x."""
     return BatchedModel.from_xml_string(single_body_xml("sphere", [0.2], plane_euler=(theta, 0, 0), name="ball"),

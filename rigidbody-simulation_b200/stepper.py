@@ -43,7 +43,9 @@ def _isotropic(inertia):
     return bool(inertia[0] == inertia[1] == inertia[2])
 
 
-def _require_cuda(model):
+def _require_cuda(model, offsets_ok=False):
+    if not offsets_ok and getattr(model, "has_offset_geoms", False):
+        raise ValueError("this stepper takes every geom at its body's origin; scenes with offset geoms go through step_multi_body")
     if model.device.type != "cuda":
         raise _lib.RbsError("the steppers run on a CUDA device only (no CPU fallback)")
 
@@ -311,6 +313,61 @@ def step_multi_sphere(model, data, dt, restitution, friction, substeps=1, count=
     a = multi_sphere_args(model, data, dt, restitution, friction, substeps, count, strict_inertia, arith, list_skin_percent)
     a.stream = current_stream(model.device)
     _lib.check(_lib.load().rbs_step_multi_sphere(ctypes.byref(a)))
+
+
+# --------------------------------------------------------------------------------------------------
+# N4: multi-body scenes with spheres and boxes (SURVEY.md section 8f; new behaviour, DESIGN.md "N4")
+# --------------------------------------------------------------------------------------------------
+def body_table(model):
+    """[nfree, RBS_BODY_TABLE_WIDTH] float64 host table of the scene's free bodies (include/rbsim_b200.h)."""
+    rows = []
+    for i in model.free_ids:
+        g = model.body_geom[i]
+        if g.type not in ("sphere", "box"):
+            raise ValueError(f"geom type {g.type!r} cannot be a free body's geom")
+        size = [float(g.size[0]), 0.0, 0.0] if g.type == "sphere" else [float(v) for v in g.size[:3]]
+        bound = size[0] if g.type == "sphere" else float(np.sqrt(sum(v * v for v in size)))
+        rows.append([0.0 if g.type == "sphere" else 1.0] + size + [float(model.body_mass[i])]
+                    + [float(v) for v in model.body_inertia[i]] + [float(v) for v in g.pos] + [float(v) for v in g.quat]
+                    + [bound * (1.0 + 1e-6)])
+    return np.asarray(rows, dtype=np.float64)
+
+
+def multi_body_args(model, data, dt, restitution, friction, substeps, count=True):
+    _require_cuda(model, offsets_ok=True)
+    if data.layout != "body":
+        raise ValueError("the multi-body step needs BatchedData(model, layout='body')")
+    if model.plane_normal is None:
+        raise ValueError("scene has no plane geom")
+    if data.nfree > 256:
+        raise ValueError("the multi-body step handles at most 256 bodies per environment")
+    host = body_table(model)                       # re-read every call: model.body_mass[...] = ... between steps takes effect
+    cached = getattr(model, "_body_table_cache", None)
+    if cached is None or not np.array_equal(cached[0], host):
+        cached = (host, torch.as_tensor(host, dtype=model.dtype).to(model.device).contiguous())
+        model._body_table_cache = cached
+    cache = cached[1]
+    a = _lib.MultiBodyArgs()
+    a.dtype, a.substeps, a.n_body = rbs_dtype(model.dtype), int(substeps), data.nfree
+    a.has_offset = int(model.has_offset_geoms)
+    a.n_env, a.stride = data.nenv, data.stride
+    a.state = _ptr(data.state)
+    a.body_table = _ptr(cache)
+    a.plane_point = _lib.D3(*model.plane_point)
+    a.plane_normal = _lib.D3(*model.plane_normal)
+    a.gravity = _lib.D3(*[float(g) for g in model.opt.gravity])
+    a.dt, a.restitution, a.friction = float(dt), float(restitution), float(friction)
+    a.n_contacts = _ptr(data.n_contacts) if count else None
+    a.n_impulses = _ptr(data.n_impulses) if count else None
+    return a
+
+
+def step_multi_body(model, data, dt, restitution, friction, substeps=1, count=True):
+    """The repaired ``custom_step_multi_sphere`` loop (multi_sphere_bounce.py:42-92) for scenes whose free bodies are
+    spheres AND boxes, geoms optionally offset in their body's frame; strict arithmetic, literal world inertia."""
+    a = multi_body_args(model, data, dt, restitution, friction, substeps, count)
+    a.stream = current_stream(model.device)
+    _lib.check(_lib.load().rbs_step_multi_body(ctypes.byref(a)))
 
 
 # --------------------------------------------------------------------------------------------------

@@ -123,3 +123,26 @@ def multi_sphere(count, n_body=64, start=0, seed=SEED, friction=0.0):
     qvel[:, :, :3] = f.u(-1, 1, (n_body, 3))
     return dict(qpos=qpos.reshape(count, 7 * n_body), qvel=qvel.reshape(count, 6 * n_body), restitution=1.0,
                 friction=friction, radius=0.1, dt=0.01, n_body=n_body)
+
+
+def multi_body(count, bodies, start=0, seed=SEED, pitch=1.0):
+    """N4 test / bench scene: len(bodies) spheres and boxes (the dicts of scenes.multi_body_xml) on a jittered cubic
+    lattice of ``pitch`` above the plane, random orientations, linear and angular velocities, so that sphere-box and
+    box-box contacts happen within the first few hundred steps."""
+    n_body = len(bodies)
+    side = 1
+    while side ** 3 < n_body:
+        side += 1
+    cells = np.stack(np.meshgrid(*[np.arange(side)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n_body]
+    f = _Fields(seed, start, count, 700)
+    pos = cells[None].astype(np.float64) * pitch + f.u(-0.1 * pitch, 0.1 * pitch, (n_body, 3))
+    pos[:, :, 2] += 0.9 * pitch
+    qpos = np.zeros((count, n_body, 7))
+    qpos[:, :, :3] = pos
+    quat = np.stack([f.unit_quat() for _ in range(n_body)], axis=1)
+    qpos[:, :, 3:] = quat
+    qvel = np.zeros((count, n_body, 6))
+    qvel[:, :, :3] = f.u(-1, 1, (n_body, 3))
+    qvel[:, :, 3:] = f.u(-2, 2, (n_body, 3))
+    return dict(qpos=qpos.reshape(count, 7 * n_body), qvel=qvel.reshape(count, 6 * n_body), n_body=n_body)
+

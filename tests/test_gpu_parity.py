@@ -1425,3 +1425,127 @@ def test_fused_fast_kernels_degenerate_inputs(rb, dtype):
     if dtype == np.float64:
         assert (calls[ok, 0] == cnt[0][ok]).all() and (imps[ok, 0] == cnt[1][ok]).all()
     assert cnt[0][ok].sum() > 50
+
+
+# ------------------------------------------------------------------------------------ N4: spheres and boxes in one scene
+MIXED_BODIES = ([{"type": "box", "size": [0.4, 0.4, 0.4]}, {"type": "sphere", "size": [0.2]}, {"type": "box", "size": [0.3, 0.2, 0.25]},
+                 {"type": "sphere", "size": [0.25]}, {"type": "box", "size": [0.35, 0.35, 0.15]}, {"type": "sphere", "size": [0.15]},
+                 {"type": "box", "size": [0.2, 0.45, 0.3]}, {"type": "sphere", "size": [0.3]}])
+
+
+def _multi_body_case(bodies, E, dtype, plane_euler=(0.0, 0.0, 0.0), pitch=0.8):
+    import rigidbody_simulation_b200.mj as mj
+    from rigidbody_simulation_b200 import scenes, stepper, synth
+    B = len(bodies)
+    s = synth.multi_body(E, bodies, pitch=pitch)
+    model = mj.MjModel.from_xml_string(scenes.multi_body_xml(bodies, plane_euler=plane_euler), nenv=E, dtype=tdt(dtype))
+    data = mj.MjData(model, layout="body")
+    data.set_state(s["qpos"], s["qvel"])
+    tab = stepper.body_table(model)
+    okw = dict(gtype=tab[:, 0].astype(np.int32), mass=tab[:, 4], inertia=tab[:, 5:8], size=tab[:, 1:4], plane_pos=model.plane_point,
+               plane_normal=model.plane_normal, gravity=G, geom_pos=tab[:, 8:11] if model.has_offset_geoms else None,
+               geom_quat=tab[:, 11:15] if model.has_offset_geoms else None)
+    return model, data, s["qpos"].astype(dtype).reshape(E, B, 7).copy(), s["qvel"].astype(dtype).reshape(E, B, 6).copy(), okw
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, F64_STEP), (np.float32, F32_STEP)])
+@pytest.mark.parametrize("offsets", [False, True])
+def test_multi_body_spheres_and_boxes_vs_oracle(rb, dtype, tol, offsets):
+    """N4: eight bodies (four boxes, one of them anisotropic in every axis, four spheres of different radii) tumbling on
+    a lattice over a tilted ground -- plane-sphere, plane-box, sphere-sphere, sphere-box and box-box contacts all occur --
+    against the C oracle's restatement of the same loop: double is bit for bit over 400 steps with every per-body counter
+    equal; float meets the per-step bar.  ``offsets``: every geom placed off its body's origin and axes (N1 remainder)."""
+    from rigidbody_simulation_b200 import stepper
+    bodies = [dict(b) for b in MIXED_BODIES]
+    if offsets:
+        for i, b in enumerate(bodies):
+            b["geom_pos"] = [0.05 * ((i % 3) - 1), 0.03 * (i % 2), -0.04 * (i % 4 == 1)]
+            b["geom_euler"] = [0.1 * i, -0.2, 0.05 * i]
+    E, B = 3000, len(bodies)
+    model, data, qp, qv, okw = _multi_body_case(bodies, E, dtype, plane_euler=(0.15, -0.1, 0.0))
+    assert model.has_offset_geoms == offsets
+    cnt = (np.zeros((E, B), np.uint32), np.zeros((E, B), np.uint32))
+    done = 0
+    for upto in (1, 10, 400):
+        co.step_multi_body(qp, qv, upto - done, dt=0.005, restitution=0.2, friction=0.6, counters=cnt, **okw)
+        stepper.step_multi_body(model, data, 0.005, 0.2, 0.6, substeps=upto - done)
+        done = upto
+        gq, gv = state_of(data)
+        if dtype == np.float64:
+            assert np.array_equal(gq, qp.reshape(E, -1)) and np.array_equal(gv, qv.reshape(E, -1)), upto
+        elif upto == 1:
+            assert max(comp_rel_err(gq.ravel(), qp.ravel(), 1e-3), comp_rel_err(gv.ravel(), qv.ravel(), 1e-3)) <= tol
+    calls, imps = data.counters()
+    if dtype == np.float64:
+        assert np.array_equal(calls, cnt[0]) and np.array_equal(imps, cnt[1])
+    assert cnt[0].sum() > 20 * E * B                                  # contacts are exercised ...
+    assert (cnt[0][:, 1::2].sum(axis=0) > 0).all() and (cnt[0][:, 0::2].sum(axis=0) > 0).all()   # ... by every body
+
+
+def test_multi_body_pair_types_all_occur_and_identities(rb):
+    """(1) Every pair type of N4 is exercised: scenes of two bodies where the only possible non-ground contact is the
+    pair itself (sphere on box, box on sphere, box on box) produce more calls than the ground alone could, bit for bit the
+    oracle.  (2) Identities that pin the new kernel to reference-pinned ones: all spheres == step_multi_sphere (strict),
+    one box == step_body_plane (strict box kernel) -- states and counters bit for bit."""
+    import rigidbody_simulation_b200.mj as mj
+    from rigidbody_simulation_b200 import scenes, stepper, synth
+    from rigidbody_simulation_b200.src.simulation import multi_sphere_bounce as ms
+    E = 2048
+    big, small, ball = {"type": "box", "size": [0.8, 0.8, 0.4]}, {"type": "box", "size": [0.4, 0.4, 0.4]}, {"type": "sphere", "size": [0.2]}
+    for bodies in ([big, ball], [ball, big], [big, small], [small, big]):
+        B = 2
+        model = mj.MjModel.from_xml_string(scenes.multi_body_xml(bodies), nenv=E, dtype=torch.float64)
+        data = mj.MjData(model, layout="body")
+        f = synth._Fields(synth.SEED, 0, E, 900)
+        qpos = np.zeros((E, B, 7)); qvel = np.zeros((E, B, 6))
+        low, high = (0, 1) if bodies[0]["size"][0] == 0.8 else (1, 0)        # the big box rests on the ground, the other falls on it
+        qpos[:, low, :3] = [0, 0, 0.4]; qpos[:, low, 3] = 1
+        qpos[:, high, :2] = f.u(-0.5, 0.5, (2,)); qpos[:, high, 2] = f.u(1.3, 2.0); qpos[:, high, 3:] = f.unit_quat()
+        qvel[:, high, 3:] = f.u(-1, 1, (3,))
+        data.set_state(qpos.reshape(E, -1), qvel.reshape(E, -1))
+        tab = stepper.body_table(model)
+        cnt = (np.zeros((E, B), np.uint32), np.zeros((E, B), np.uint32))
+        qp, qv = qpos.copy(), qvel.copy()
+        co.step_multi_body(qp, qv, 300, gtype=tab[:, 0].astype(np.int32), mass=tab[:, 4], inertia=tab[:, 5:8], size=tab[:, 1:4],
+                           plane_pos=[0, 0, 0], plane_normal=[0, 0, 1], gravity=G, dt=0.005, restitution=0.2, friction=0.6, counters=cnt)
+        stepper.step_multi_body(model, data, 0.005, 0.2, 0.6, substeps=300)
+        gq, gv = state_of(data)
+        assert np.array_equal(gq, qp.reshape(E, -1)) and np.array_equal(gv, qv.reshape(E, -1)), bodies
+        calls, imps = data.counters()
+        assert np.array_equal(calls, cnt[0]) and np.array_equal(imps, cnt[1])
+        # The A9 loop never flips the normal (geom1 -> geom2, geom1 = the lower index), so only the HIGHER-index body of a
+        # pair responds to an approach (SURVEY section 8 row A9): falling with the higher index it is caught by the box and
+        # never reaches the ground within 300 steps -- all its calls are pair contacts; falling with the lower index it
+        # registers the pair contacts (calls) but gets no impulse from them and ends on the ground.
+        above = qp[:, high, 2] > 0.8 + 0.15
+        if high > low:
+            assert above.mean() > 0.5 and (cnt[0][above, high] > 0).mean() > 0.9, (bodies, above.mean())
+        else:
+            assert above.mean() < 0.1 and (cnt[0][:, high] > cnt[1][:, high]).mean() > 0.9, (bodies, above.mean())
+    # all spheres == the strict multi-sphere kernel
+    B, E = 27, 1500
+    s = synth.multi_sphere(E, n_body=B, friction=0.3)
+    m1, d1 = ms.build(E, n_body=B, dtype=torch.float64)
+    d1.set_state(s["qpos"], s["qvel"])
+    stepper.step_multi_sphere(m1, d1, 0.01, 1.0, 0.3, substeps=80, arith="strict")
+    m2 = mj.MjModel.from_xml_string(scenes.multi_body_xml([{"type": "sphere", "size": [0.1]}] * B, timestep=0.01), nenv=E, dtype=torch.float64)
+    d2 = mj.MjData(m2, layout="body")
+    d2.set_state(s["qpos"], s["qvel"])
+    stepper.step_multi_body(m2, d2, 0.01, 1.0, 0.3, substeps=80)
+    for a, b in zip(state_of(d1) + d1.counters(), state_of(d2) + d2.counters()):
+        assert np.array_equal(a, b)
+    assert d1.counters()[0].sum() > E * B
+    # one box == the strict single-body box kernel (threshold 0: the multi-body loop has none, like multi_sphere_bounce.py)
+    E = 4096
+    sc = synth.cube(E, kind="bounce")
+    m3 = scenes.cube_on_plane(E, theta=0.0, dtype=torch.float64)
+    d3 = rb.BatchedData(m3)
+    d3.set_state(sc["qpos"], sc["qvel"])
+    stepper.step_body_plane(m3, d3, -1, 0.009, 0.2, 0.6, 0.0, substeps=300, arith="strict")
+    m4 = mj.MjModel.from_xml_string(scenes.multi_body_xml([{"type": "box", "size": [0.4, 0.4, 0.4]}], timestep=0.009), nenv=E, dtype=torch.float64)
+    d4 = mj.MjData(m4, layout="body")
+    d4.set_state(sc["qpos"], sc["qvel"])
+    stepper.step_multi_body(m4, d4, 0.009, 0.2, 0.6, substeps=300)
+    for a, b in zip(state_of(d3) + d3.counters(), state_of(d4) + d4.counters()):
+        assert np.array_equal(a, b)
+    assert d3.counters()[0].sum() > E

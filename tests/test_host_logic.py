@@ -253,10 +253,28 @@ def test_parser_orientation_specifiers_units_and_defaults():
                 '<mujoco><worldbody><body><freejoint/><geom type="sphere" size="0.2"/><inertial pos="0 0 0.1" mass="1" diaginertia="1 1 1"/></body></worldbody></mujoco>',
                 '<mujoco><worldbody><body><joint type="hinge"/><geom type="sphere" size="0.2"/></body></worldbody></mujoco>',
                 '<mujoco><worldbody><body><freejoint/><geom type="box" size="0.2"/></body></worldbody></mujoco>',
-                '<mujoco><default><default class="a"/></default><worldbody/></mujoco>',
-                '<mujoco><worldbody><body><freejoint/><geom type="sphere" size="0.2" pos="0 0 0.1"/></body></worldbody></mujoco>'):
+                '<mujoco><default><default class="a"/></default><worldbody/></mujoco>'):
         with pytest.raises(ValueError):
             mjcf.parse_string(bad)
+    # a geom offset from its free body's origin parses (N1 remainder); only the multi-body stepper takes such a scene
+    import rigidbody_simulation_b200 as rb
+    from rigidbody_simulation_b200 import stepper
+    off = ('<mujoco><worldbody><geom type="plane" size="1 1 1"/><body pos="0 0 1"><freejoint/>'
+           '<geom type="box" size="0.1 0.2 0.3" pos="0 0 0.1" euler="0.2 0 0" density="50"/></body></worldbody></mujoco>')
+    sc = mjcf.parse_string(off.replace("<mujoco>", '<mujoco><compiler angle="radian"/>'))
+    g = sc.geoms[sc.bodies[1].geoms[0]]
+    assert g.pos == [0.0, 0.0, 0.1] and g.quat == pytest.approx([math.cos(0.1), math.sin(0.1), 0, 0], abs=1e-15)
+    model = rb.BatchedModel(sc, nenv=2, device="cpu")
+    assert model.has_offset_geoms
+    tab = stepper.body_table(model)
+    assert tab.shape == (1, 16) and tab[0, 0] == 1.0 and list(tab[0, 1:4]) == [0.1, 0.2, 0.3] and list(tab[0, 8:11]) == [0.0, 0.0, 0.1]
+    assert tab[0, 15] == pytest.approx(math.sqrt(0.14) * (1 + 1e-6), rel=1e-15)
+    for layout, fn, args in (("env", stepper.body_plane_args, (-1, 0.01, 1.0, 0.5, 0.0, 0, 1)),
+                             ("body", stepper.multi_sphere_args, (0.01, 1.0, 0.0, 1))):
+        with pytest.raises(ValueError, match="offset"):
+            fn(model, rb.BatchedData(model, layout=layout), *args)
+    with pytest.raises(rb.RbsError):                                       # and no CPU fallback for the one that does
+        stepper.multi_body_args(model, rb.BatchedData(model, layout="body"), 0.01, 1.0, 0.5, 1)
 
 
 def test_cli_help_and_headless_flags():
