@@ -57,6 +57,7 @@ Option g_options[] = {
     {"box_compact", "RBS_BOX_COMPACT", {0}, 0},              // plane-frame box kernel: CTA-level compaction of contacts (measured slower: off)
     {"tb_minb", "RBS_TB_MINB", {0}, 0},                      // resident CTAs per SM of the two-ball fast kernel (5, 6 or 8; 0 = 6 in double, 8 in float)
     {"tb_packed", "RBS_TB_PACKED", {0}, 0},                  // float two-ball fast stepper: packed fp32x2 kernel, two envs per thread (1) or scalar (0: measured equal, fewer ragged waves)
+    {"mb_minb", "RBS_MB_MINB", {0}, 0},                      // resident CTAs per SM of the multi-body stepper (1, 2, 3; 0 = tuned)
     {"ms_skin_percent", "RBS_MS_SKIN_PERCENT", {0}, 50},     // starting skin of the adaptive partner lists
     {"ms_kernel", "RBS_MS_KERNEL", {0}, 2},                  // multi-sphere fast policy: 2 = plane-frame kernel, 1 = first generation
     {"ms_walk_cost", "RBS_MS_WALK_COST", {0}, 40},           // plane-frame multi-sphere kernel: cost of a list entry per substep (skin controller)
@@ -572,11 +573,22 @@ template <typename T> int launch_multi_body(const rbs_multi_body_args *a) {
     p.n_impulses = a->n_impulses;
     const int threads = ((p.env_per_block * B + 31) / 32) * 32;
     const size_t smem = ((size_t)B * rbs::kBodyTable + 2 * (size_t)p.env_per_block * B * 12) * sizeof(T);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(rbs::step_multi_body_kernel<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(RBS_ECUDA, "rbs_step_multi_body: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
-    }
-    rbs::step_multi_body_kernel<T, 256><<<blocks_for(a->n_env, p.env_per_block), threads, smem, as_stream(a->stream)>>>(p);
+    // resident CTAs per SM (option mb_minb: 1 = uncapped registers, 2 = 128, 3 = 80; 0 = tuned default)
+    int minb = (int)option("mb_minb");
+    if (minb == 0) minb = sizeof(T) == 8 ? 2 : 3;            // profiles/r2_multi_body.jsonl
+#define RBS_MB_LAUNCH(KERNEL)                                                                                              \
+    do {                                                                                                                   \
+        if (smem > 48 * 1024) {                                                                                            \
+            cudaError_t e__ = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+            if (e__ != cudaSuccess)                                                                                        \
+                return fail(RBS_ECUDA, "rbs_step_multi_body: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e__)); \
+        }                                                                                                                  \
+        KERNEL<<<blocks_for(a->n_env, p.env_per_block), threads, smem, as_stream(a->stream)>>>(p);                          \
+    } while (0)
+    if (minb >= 3) RBS_MB_LAUNCH((rbs::step_multi_body_kernel<T, 256, 3>));
+    else if (minb == 2) RBS_MB_LAUNCH((rbs::step_multi_body_kernel<T, 256, 2>));
+    else RBS_MB_LAUNCH((rbs::step_multi_body_kernel<T, 256, 1>));
+#undef RBS_MB_LAUNCH
     return check_launch("rbs_step_multi_body");
 }
 
