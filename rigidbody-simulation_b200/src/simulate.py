@@ -25,8 +25,9 @@ import os
 import sys
 import time
 
-SIMULATIONS = ["cube_incline", "ball_collision", "single_sphere", "compare_builtin", "multi_sphere"]
-DEFAULT_STEPS = {"single_sphere": 2000, "cube_incline": 240, "ball_collision": 500, "multi_sphere": 300}
+SIMULATIONS = ["cube_incline", "ball_collision", "single_sphere", "compare_builtin", "multi_sphere"]   # src/simulate.py:13-19
+NEW_SIMULATIONS = ["mixed_pile"]          # not in the reference: spheres and boxes in one scene
+DEFAULT_STEPS = {"single_sphere": 2000, "cube_incline": 240, "ball_collision": 500, "multi_sphere": 300, "mixed_pile": 400}
 
 
 def _rank_world():
@@ -67,10 +68,10 @@ def build_random(sim_name, count, start, seed, device, tdtype, bodies=64):
 
 def run_simulation(sim_name, steps=None, envs=1, dtype="fp64", substeps=1, device=None, log_path=None, arith="strict",
                    config=None, seed=None, bodies=64):
-    if sim_name not in SIMULATIONS:
+    if sim_name not in SIMULATIONS + NEW_SIMULATIONS:
         print(f"Unknown simulation name: '{sim_name}'")
         print("Available simulations:")
-        for sim in SIMULATIONS:
+        for sim in SIMULATIONS + NEW_SIMULATIONS:
             print(f"  {sim}")
         sys.exit(1)
     if sim_name == "compare_builtin":
@@ -112,8 +113,17 @@ def run_simulation(sim_name, steps=None, envs=1, dtype="fp64", substeps=1, devic
     K = max(1, int(substeps))
     t0 = time.time()
     logger = None
+    if sim_name == "mixed_pile":
+        if arith != "strict":
+            print("mixed_pile runs the strict policy only (boxes of any shape need the literal world inertia)")
+            sys.exit(1)
+        config = "random"
     if count == 0:
         model = data = None
+    elif sim_name == "mixed_pile":
+        from .simulation import mixed_pile
+        model, data, logger = mixed_pile.run_headless(steps, count, device, tdtype, K, n_body=min(bodies, 256), start=start,
+                                                      seed=synth.SEED if seed is None else seed)
     elif config == "random":
         if log_path is not None:
             print("--log records the shipped scenarios (single_sphere, cube_incline); it is not available with --config random")
@@ -164,7 +174,7 @@ def run_simulation(sim_name, steps=None, envs=1, dtype="fp64", substeps=1, devic
 
 def main(argv=None):
     parser = argparse.ArgumentParser(description="Headless rigid-body simulation runner (B200)")
-    parser.add_argument("--sim", type=str, required=True, help="one of: " + ", ".join(SIMULATIONS))
+    parser.add_argument("--sim", type=str, required=True, help="one of: " + ", ".join(SIMULATIONS + NEW_SIMULATIONS))
     parser.add_argument("--headless", action="store_true", help="accepted for clarity; this runner is always headless")
     parser.add_argument("--steps", type=int, default=None)
     parser.add_argument("--envs", type=int, default=1, help="environments in total (sharded over --gpus)")
@@ -175,7 +185,8 @@ def main(argv=None):
     parser.add_argument("--config", choices=["shipped", "random"], default=None,
                         help="initial conditions: the script's own (default) or the randomised BASELINE config (default with --seed)")
     parser.add_argument("--seed", type=int, default=None, help="seed of the randomised initial states (implies --config random)")
-    parser.add_argument("--bodies", type=int, default=64, help="spheres per environment of the randomised multi_sphere config")
+    parser.add_argument("--bodies", type=int, default=None,
+                        help="bodies per environment: spheres of the randomised multi_sphere config (default 64), spheres and boxes of mixed_pile (default 8)")
     parser.add_argument("--gpus", type=int, default=1, help="one process per GPU; environments are sharded, no collective on the step path")
     parser.add_argument("--log", type=str, default=None, metavar="PATH.npz",
                         help="save times [n] and positions [n, sampled envs, 3] of every step (recorded on the device, also "
@@ -195,7 +206,7 @@ def main(argv=None):
         print(f"--gpus {args.gpus} does not match the launcher's WORLD_SIZE={os.environ['WORLD_SIZE']}")
         sys.exit(1)
     run_simulation(args.sim, args.steps, args.envs, args.dtype, args.substeps_per_launch, log_path=args.log, arith=args.arith,
-                   config=args.config, seed=args.seed, bodies=args.bodies)
+                   config=args.config, seed=args.seed, bodies=args.bodies if args.bodies is not None else (8 if args.sim == "mixed_pile" else 64))
 
 
 if __name__ == "__main__":

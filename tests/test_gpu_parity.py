@@ -1549,3 +1549,22 @@ def test_multi_body_pair_types_all_occur_and_identities(rb):
     for a, b in zip(state_of(d3) + d3.counters(), state_of(d4) + d4.counters()):
         assert np.array_equal(a, b)
     assert d3.counters()[0].sum() > E
+
+
+def test_mixed_pile_cli_and_shard_invariance(rb, capsys):
+    """The N4 scenario through the CLI: `--sim mixed_pile` prints the one JSON line with finite statistics and contacts,
+    and its environments are a pure function of the global index -- environments [3, 7) of a 10-env run computed as
+    their own shard (start = 3) are bit for bit the same states."""
+    import json
+    from rigidbody_simulation_b200.src import simulate
+    from rigidbody_simulation_b200.src.simulation import mixed_pile
+    out = simulate.run_simulation("mixed_pile", steps=120, envs=10, substeps=40, bodies=8)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["sim"] == "mixed_pile" and line["config"] == "random" and line["contacts"] > 0 and line["impulses"] > 0
+    assert np.isfinite(line["stats"]["energy_sum"]) and 0.0 < line["stats"]["max_height"] < 20.0
+    _, whole, _ = mixed_pile.run_headless(120, 10, substeps=40)
+    _, part, _ = mixed_pile.run_headless(120, 4, substeps=40, start=3)
+    assert out["qpos_env0"] == whole.qpos.torch().cpu().numpy()[0].tolist()
+    assert np.array_equal(whole.qpos.torch().cpu().numpy()[3:7], part.qpos.torch().cpu().numpy())
+    with pytest.raises(SystemExit):
+        simulate.run_simulation("mixed_pile", steps=10, envs=2, arith="fast")
