@@ -65,6 +65,8 @@ Option g_options[] = {
     {"ms_regs", "RBS_MS_REGS", {0}, 96},                     // register cap of the frictionless plane-frame multi-sphere kernel (96 or 128)
     {"probe_mode", "RBS_PROBE_MODE", {0}, 1},                // rbs_fma_probe operand mode
     {"host_chunks", "RBS_HOST_CHUNKS", {0}, 16},             // pipeline depth of rbs_run_body_plane_host
+    {"host_streams", "RBS_HOST_STREAMS", {0}, 3},            // compute streams of the host-buffer pipeline = chunks stepped concurrently (1..4; profiles/r2_ab_host_pipeline.jsonl)
+    {"host_wave_ctas", "RBS_HOST_WAVE_CTAS", {0}, 0},        // CTAs per SM that make one chunk quantum of rbs_run_body_plane_host (0 = 4)
 };
 std::once_flag g_options_once;
 Option *find_option(const char *name) {
@@ -653,6 +655,7 @@ int launch_multi_sphere_any(const rbs_multi_sphere_args *a, const Window &w) {
 // nothing and run concurrently; calls on the same device are serialised by that device's mutex (they would contend for
 // the same copy engines anyway).  Nothing else in the library keeps state between calls.
 constexpr int kMaxChunks = 32;
+constexpr int kMaxComputeStreams = 4;
 constexpr int kMaxDevices = 64;
 struct Pipe {
     std::mutex mutex;
@@ -660,7 +663,7 @@ struct Pipe {
     int sm_count = 148;
     void *ws = nullptr;
     size_t ws_bytes = 0;
-    cudaStream_t in = nullptr, out = nullptr, compute[2] = {nullptr, nullptr};
+    cudaStream_t in = nullptr, out = nullptr, compute[kMaxComputeStreams] = {};
     cudaEvent_t start = nullptr, finished = nullptr, arrived[kMaxChunks] = {}, stepped[kMaxChunks] = {};
 };
 Pipe g_pipes[kMaxDevices];
@@ -707,8 +710,7 @@ int pipe_init(Pipe &pp) {
     ok(cudaDeviceGetAttribute(&pp.sm_count, cudaDevAttrMultiProcessorCount, dev));
     ok(cudaStreamCreateWithFlags(&pp.in, cudaStreamNonBlocking));
     ok(cudaStreamCreateWithFlags(&pp.out, cudaStreamNonBlocking));
-    ok(cudaStreamCreateWithFlags(&pp.compute[0], cudaStreamNonBlocking));
-    ok(cudaStreamCreateWithFlags(&pp.compute[1], cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxComputeStreams; ++i) ok(cudaStreamCreateWithFlags(&pp.compute[i], cudaStreamNonBlocking));
     ok(cudaEventCreateWithFlags(&pp.start, cudaEventDisableTiming));
     ok(cudaEventCreateWithFlags(&pp.finished, cudaEventDisableTiming));
     for (int i = 0; i < kMaxChunks; ++i) {
@@ -782,6 +784,9 @@ int run_host_pipelined(const Args *a, int n_body, int body_fastest, long envs_pe
         for (long done = 0; done < middle; done += per) offs[n_chunks + 1] = offs[n_chunks] + (middle - done < per ? middle - done : per), ++n_chunks;
         offs[n_chunks + 1] = E, ++n_chunks;
     }
+    long n_streams = option("host_streams");                 // chunks in flight on the GPU at once
+    if (n_streams < 1) n_streams = 1;
+    if (n_streams > kMaxComputeStreams) n_streams = kMaxComputeStreams;
     cudaStream_t user = as_stream(a->stream);
     RBS_CUDA(cudaEventRecord(g_pipe.start, user));
     RBS_CUDA(cudaStreamWaitEvent(g_pipe.in, g_pipe.start, 0));
@@ -793,7 +798,7 @@ int run_host_pipelined(const Args *a, int n_body, int body_fastest, long envs_pe
     }
     for (int c = 0; c < n_chunks; ++c) {
         const long off = offs[c], cnt = offs[c + 1] - offs[c];
-        cudaStream_t cs = g_pipe.compute[c & 1];
+        cudaStream_t cs = g_pipe.compute[c % n_streams];
         char *state_c = state_d + (size_t)off * 13 * per_env;
         char *qp_c = qpos_d + (size_t)off * 7 * per_env, *qv_c = qvel_d + (size_t)off * 6 * per_env;
         const long stride_c = body_fastest ? cnt * n_body : cnt;
@@ -1042,7 +1047,8 @@ int rbs_run_body_plane_host(const rbs_body_plane_args *a, void *qpos_host, void 
     int rc = validate_body_plane(a, false);
     if (rc) return rc;
     if (a->trajectory) return fail(RBS_EINVAL, "rbs_run_body_plane_host: trajectory sampling needs device-resident stepping");
-    return run_host_pipelined(a, 1, 0, 4L * rbs::kBlock, qpos_host, qvel_host, total_steps, launch_body_plane_any);
+    const long wave_ctas = option("host_wave_ctas") > 0 ? option("host_wave_ctas") : 4;
+    return run_host_pipelined(a, 1, 0, wave_ctas * rbs::kBlock, qpos_host, qvel_host, total_steps, launch_body_plane_any);
 }
 
 int rbs_run_two_ball_host(const rbs_two_ball_args *a, void *qpos_host, void *qvel_host, long total_steps) {
