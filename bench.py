@@ -528,6 +528,51 @@ def b200_arm(args):
 
     results = {n: measure(n, n == args.config) for n in names}
 
+    def measure_mixed_pile():
+        """SURVEY section 8(f) row N4 (not a BASELINE config): eight spheres and boxes per environment, 131,072 environments
+        per GPU, 512 substeps from the scenario's initial pile in launches of 64; strict policy (the only one this stepper
+        has), counters on; the C oracle's restatement of the same loop on all host cores beside it (rank 0, bounded sample)."""
+        from rigidbody_simulation_b200.src.simulation import mixed_pile
+        E, B, S, F = 131072, 8, 512, 64
+        model, data = mixed_pile.build(E, device=dev, dtype=tdtype, n_body=B, start=rank * E)
+        s0 = data.state.clone()
+
+        def reset():
+            data.state.copy_(s0)
+
+        def step():
+            for _ in range(S // F):
+                stepper.step_multi_body(model, data, mixed_pile.timestep, mixed_pile.restitution_coefficient,
+                                        mixed_pile.friction_coefficient, substeps=F, count=True)
+        ms, _, _ = timed(step, 2, 1, before=reset)
+        calls, imps = data.counters()
+        out = {"workload": "mixed_pile: 4 boxes (one cube of models/cube.xml, three anisotropic) + 4 spheres per environment, random pile "
+                           "over a flat plane, plane-sphere / plane-box / sphere-sphere / sphere-box / box-box contacts, e=0.2, mu=0.6, dt=0.005",
+               "envs_per_gpu": E, "bodies_per_env": B, "substeps_per_step": S, "substeps_fused_per_launch": F, "arith": "strict",
+               "value": world * E * S / (ms / 2 * 1e-3), "unit": METRIC, "body_substeps_per_s": world * E * B * S / (ms / 2 * 1e-3),
+               "contacts_per_body_substep": float(calls.sum()) / (3.0 * E * B * S), "impulses_per_body_substep": float(imps.sum()) / (3.0 * E * B * S),
+               "kernel": "step_multi_body_kernel"}
+        if rank == 0 and not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import c_oracle as co
+            import numpy as np
+            n = 32 * (os.cpu_count() or 1)
+            tab = stepper.body_table(model)
+            data.state.copy_(s0)
+            q = data.qpos.torch()[:n].cpu().numpy().astype(np.float64).reshape(n, B, 7).copy()
+            v = data.qvel.torch()[:n].cpu().numpy().astype(np.float64).reshape(n, B, 6).copy()
+            t0 = time.time()
+            co.step_multi_body(q, v, 256, gtype=tab[:, 0].astype(np.int32), mass=tab[:, 4], inertia=tab[:, 5:8], size=tab[:, 1:4],
+                               plane_pos=[0, 0, 0], plane_normal=[0, 0, 1], gravity=[0, 0, -9.8], dt=mixed_pile.timestep,
+                               restitution=mixed_pile.restitution_coefficient, friction=mixed_pile.friction_coefficient)
+            out["cpu_baseline"] = {"value": n * 256 / (time.time() - t0), "unit": METRIC, "cores": co.max_threads(), "kind": "port",
+                                   "sample": f"{n} environments x 256 steps of the C restatement (OpenMP); the reference has no such scene"}
+        return out
+
+    extra = {}
+    if not args.no_other_configs:
+        extra["mixed_pile"] = measure_mixed_pile()
+
     if rank == 0:
         h = results[args.config]
         line = {"metric": METRIC, "value": h["value"], "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -542,6 +587,8 @@ def b200_arm(args):
             line["cpu_baseline_native"] = cpu_native
         line["configs"] = {n: {k: v for k, v in r.items() if k not in ("clocks", "gpu_launches", "end_of_run_stats", "host_link")}
                            for n, r in results.items()}
+        if extra:
+            line["extra"] = extra                            # beyond BASELINE.json: SURVEY section 8(f) rows
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
