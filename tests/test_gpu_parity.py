@@ -1568,3 +1568,25 @@ def test_mixed_pile_cli_and_shard_invariance(rb, capsys):
     assert np.array_equal(whole.qpos.torch().cpu().numpy()[3:7], part.qpos.torch().cpu().numpy())
     with pytest.raises(SystemExit):
         simulate.run_simulation("mixed_pile", steps=10, envs=2, arith="fast")
+
+
+@pytest.mark.parametrize("B,E", [(70, 37), (256, 5), (3, 1001), (1, 130)])
+def test_multi_body_shapes_vs_oracle(rb, B, E):
+    """Launch shapes of the multi-body stepper: more than 64 bodies (several words of the broad-phase bitmask, B = 70 is
+    also not a divisor of the CTA size), the ABI maximum of 256 bodies (one environment per CTA, more than 48 KB of
+    shared memory), odd environment counts (ragged last CTA), a single body; bit for bit the oracle, counters included."""
+    from rigidbody_simulation_b200 import stepper
+    bodies = [dict(MIXED_BODIES[i % len(MIXED_BODIES)]) for i in range(B)]
+    model, data, qp, qv, okw = _multi_body_case(bodies, E, np.float64, pitch=0.8)
+    cnt = (np.zeros((E, B), np.uint32), np.zeros((E, B), np.uint32))
+    steps = 60 if B >= 70 else 200
+    co.step_multi_body(qp, qv, steps, dt=0.005, restitution=0.2, friction=0.6, counters=cnt, **okw)
+    for k in (steps // 2, steps - steps // 2):
+        stepper.step_multi_body(model, data, 0.005, 0.2, 0.6, substeps=k)
+    gq, gv = state_of(data)
+    assert np.array_equal(gq, qp.reshape(E, -1)) and np.array_equal(gv, qv.reshape(E, -1))
+    calls, imps = data.counters()
+    assert np.array_equal(calls, cnt[0]) and np.array_equal(imps, cnt[1])
+    assert cnt[0].sum() > 0
+    with pytest.raises(ValueError):
+        stepper.step_multi_body(model, data, 0.005, 0.2, 0.6, substeps=0)
