@@ -215,3 +215,62 @@ def test_fast_cached_args_follow_model_edits(rb):
     e_host.fill_(1.0)
     stepper.step_body_plane(model, data, -1, s["dt"], e_host, None, 0.0, substeps=8)
     assert not torch.equal(data.state, a)
+
+
+def test_strict_policy_every_other_config_at_baseline_size_is_bit_for_bit_the_oracle(rb):
+    """The exact-count contract (north_star: "contact-event counts must match exactly") at the sizes BASELINE.json names,
+    for the configs the test above does not cover: two balls (configs[2], 1,048,576 environments x 2048 steps), the cube
+    bouncing and on the incline (configs[3], 1,048,576 x 512 / 256 steps) and 64 spheres (configs[4], all 65,536
+    environments x 64 steps from the lattice, the dense phase).  Strict policy, fused launches, counters on: states and
+    every per-environment / per-body counter equal the C oracle's bit for bit."""
+    from rigidbody_simulation_b200 import scenes, stepper, synth
+    from rigidbody_simulation_b200.src.simulation import ball_collision, multi_sphere_bounce
+    E = E_BENCH
+    # configs[2]
+    s = synth.two_ball(E)
+    model, data = ball_collision.build(E, device="cuda:0", dtype=torch.float64)
+    data.set_state(s["qpos"], s["qvel"])
+    qp, qv = s["qpos"].copy(), s["qvel"].copy()
+    cnt = (np.zeros(E, np.uint32), np.zeros(E, np.uint32))
+    co.step_two_ball(qp, qv, HORIZON, mass=model.body_mass[1], radius=0.1, gravity=G, dt=0.01, restitution=1.0, friction=0.3, counters=cnt)
+    for _ in range(HORIZON // FUSE):
+        stepper.step_two_ball(model, data, 0.01, 1.0, 0.3, radius=0.1, substeps=FUSE, count=True, arith="strict")
+    gq, gv = _state(data)
+    assert np.array_equal(gq, qp) and np.array_equal(gv, qv)
+    ground, pair = data.counters()
+    assert np.array_equal(ground[:, 0], cnt[0]) and np.array_equal(pair[:, 0], cnt[1]) and int(cnt[1].sum()) > E // 2
+    del model, data
+    # configs[3]
+    for kind, steps in (("bounce", 512), ("incline", 256)):
+        s = synth.cube(E, kind=kind)
+        model = scenes.cube_on_plane(E, theta=s["theta"], device="cuda:0", dtype=torch.float64)
+        data = rb.BatchedData(model)
+        data.set_state(s["qpos"], s["qvel"])
+        qp, qv = s["qpos"].copy(), s["qvel"].copy()
+        cnt = (np.zeros(E, np.uint32), np.zeros(E, np.uint32))
+        co.step_body_plane(qp, qv, steps, geom="box", mass=model.body_mass[-1], inertia=model.body_inertia[-1], size=s["half"],
+                           plane_pos=[0, 0, 0], plane_normal=model.plane_normal, gravity=G, dt=s["dt"], restitution=s["restitution"],
+                           friction=s["friction"], threshold=s["threshold"], counters=cnt)
+        for _ in range(steps // 128):
+            stepper.step_body_plane(model, data, -1, s["dt"], s["restitution"], s["friction"], s["threshold"], substeps=128, count=True,
+                                    arith="strict")
+        gq, gv = _state(data)
+        assert np.array_equal(gq, qp) and np.array_equal(gv, qv), kind
+        calls, imps = data.counters()
+        assert np.array_equal(calls[:, 0], cnt[0]) and np.array_equal(imps[:, 0], cnt[1]), kind
+        assert int(cnt[0].sum()) > E
+        del model, data
+    # configs[4]
+    E5, B, steps = 1 << 16, 64, 64
+    s = synth.multi_sphere(E5, n_body=B, friction=0.0)
+    model, data = multi_sphere_bounce.build(E5, device="cuda:0", dtype=torch.float64, n_body=B)
+    data.set_state(s["qpos"], s["qvel"])
+    qp, qv = s["qpos"].reshape(E5, B, 7).copy(), s["qvel"].reshape(E5, B, 6).copy()
+    cnt = (np.zeros((E5, B), np.uint32), np.zeros((E5, B), np.uint32))
+    co.step_multi_sphere(qp, qv, steps, mass=model.body_mass[1], inertia=model.body_inertia[1], radius=0.1, plane_pos=[0, 0, 0],
+                         plane_normal=[0, 0, 1], gravity=G, dt=0.01, restitution=1.0, friction=0.0, counters=cnt)
+    stepper.step_multi_sphere(model, data, 0.01, 1.0, 0.0, substeps=steps, arith="strict")
+    gq, gv = _state(data)
+    assert np.array_equal(gq, qp.reshape(E5, -1)) and np.array_equal(gv, qv.reshape(E5, -1))
+    calls, imps = data.counters()
+    assert np.array_equal(calls, cnt[0]) and np.array_equal(imps, cnt[1]) and int(cnt[0].sum()) > E5 * B
