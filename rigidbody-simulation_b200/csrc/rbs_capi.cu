@@ -577,7 +577,7 @@ template <typename T> int launch_multi_body(const rbs_multi_body_args *a) {
     const size_t smem = ((size_t)B * rbs::kBodyTable + 2 * (size_t)p.env_per_block * B * 12) * sizeof(T);
     // resident CTAs per SM (option mb_minb: 1 = uncapped registers, 2 = 128, 3 = 80; 0 = tuned default)
     int minb = (int)option("mb_minb");
-    if (minb == 0) minb = sizeof(T) == 8 ? 2 : 3;            // profiles/r2_multi_body.jsonl
+    if (minb == 0) minb = 2;                                 // profiles/r2_multi_body.jsonl
 #define RBS_MB_LAUNCH(KERNEL)                                                                                              \
     do {                                                                                                                   \
         if (smem > 48 * 1024) {                                                                                            \
