@@ -151,6 +151,28 @@ def host_link_bandwidth(device, pinned, world_size=1, rank=0, reps=4):
             out.append(reps * nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
         return out
 
+    def measure_duplex():
+        """both directions at once on two streams (what the chunk pipeline of the host-buffer drivers does): GB/s per direction"""
+        other_host = torch.empty_like(pinned).pin_memory()
+        other_dev = torch.empty_like(dev_buf)
+        s_in, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        torch.cuda.synchronize(device)
+        with torch.cuda.stream(s_in):
+            dev_buf.copy_(pinned, non_blocking=True)
+            ev[0].record()
+            for _ in range(reps):
+                dev_buf.copy_(pinned, non_blocking=True)
+            ev[1].record()
+        with torch.cuda.stream(s_out):
+            other_host.copy_(other_dev, non_blocking=True)
+            ev[2].record()
+            for _ in range(reps):
+                other_host.copy_(other_dev, non_blocking=True)
+            ev[3].record()
+        torch.cuda.synchronize(device)
+        return [reps * nbytes / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9, reps * nbytes / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9]
+
     multi = dist.is_available() and dist.is_initialized() and world_size > 1
     alone = [0.0, 0.0]
     for r in range(world_size):
@@ -160,17 +182,25 @@ def host_link_bandwidth(device, pinned, world_size=1, rank=0, reps=4):
         if r == rank:
             alone = measure()
     together = alone
+    duplex = [0.0, 0.0]
+    for r in range(world_size):
+        if multi:
+            torch.cuda.synchronize(device)
+            dist.barrier()
+        if r == rank:
+            duplex = measure_duplex()
     if multi:
         torch.cuda.synchronize(device)
         dist.barrier()
         together = measure()
-        t = torch.tensor(alone + together, dtype=torch.float64, device=device)
+        t = torch.tensor(alone + together + duplex, dtype=torch.float64, device=device)
         rows = [torch.empty_like(t) for _ in range(world_size)]
         dist.all_gather(rows, t)
         table = [r.tolist() for r in rows]
     else:
-        table = [alone + together]
+        table = [alone + together + duplex]
     return {"bytes_per_copy": nbytes, "unit": "GB/s",
+            "h2d_while_d2h_alone": [round(r[4], 2) for r in table], "d2h_while_h2d_alone": [round(r[5], 2) for r in table],
             "h2d_alone": [round(r[0], 2) for r in table], "d2h_alone": [round(r[1], 2) for r in table],
             "h2d_all_ranks_together": [round(r[2], 2) for r in table], "d2h_all_ranks_together": [round(r[3], 2) for r in table],
             "aggregate_together": round(sum(r[2] + r[3] for r in table), 1)}
