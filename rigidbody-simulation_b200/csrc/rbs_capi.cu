@@ -220,6 +220,26 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
             // only the hit environments' warps in the ~890-instruction dependent chain, the path turns latency-bound).
             long compact = option("strict_compact");
             if (compact == 0) compact = GEOM == 0 ? 5 : -1;
+            if (!a->xfrc && compact >= 20) {
+                // K environments per thread (K * 128 per CTA), all warps work through the contact phase: compact = 10*K + resident CTAs
+#define RBS_CM(KK, MB)                                                                                                   \
+    do {                                                                                                                 \
+        const size_t smem__ = (size_t)(KK) * rbs::kBlock * (13 * sizeof(T) + 3 * sizeof(unsigned));                      \
+        cudaFuncSetAttribute(rbs::step_body_plane_compact_multi_kernel<T, GEOM, KK, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem__); \
+        cudaFuncSetAttribute(rbs::step_body_plane_compact_multi_kernel<T, GEOM, KK, MB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+        rbs::step_body_plane_compact_multi_kernel<T, GEOM, KK, MB><<<blocks_for(w.cnt, (KK) * rbs::kBlock), rbs::kBlock, smem__, st>>>(p); \
+    } while (0)
+                switch (compact) {
+                    case 24: RBS_CM(2, 4); return;
+                    case 25: RBS_CM(2, 5); return;
+                    case 26: RBS_CM(2, 6); return;
+                    case 34: RBS_CM(3, 4); return;
+                    case 35: RBS_CM(3, 5); return;
+                    case 43: RBS_CM(4, 3); return;
+                    default: RBS_CM(4, 4); return;
+                }
+#undef RBS_CM
+            }
             if (!a->xfrc && compact > 0) {
                 if (compact >= 8) {
                     cudaFuncSetAttribute(rbs::step_body_plane_compact_kernel<T, GEOM, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
