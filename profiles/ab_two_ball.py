@@ -21,9 +21,10 @@ s = synth.two_ball(E)
 for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
     model, data = ball_collision.build(E, device=dev, dtype=dtype)
     ref = None
-    for minb, packed in ((5, 0), (6, 0), (8, 0)) + (((4, 1), (6, 1), (8, 1)) if tag == "fp32" else ()):
+    for minb, packed, uniform in ((5, 0, 0), (6, 0, 0), (8, 0, 0), (5, 0, 1), (6, 0, 1), (8, 0, 1)) + (((6, 1, 0), (8, 1, 0)) if tag == "fp32" else ()):
         rb._lib.set_option("tb_minb", minb)
         rb._lib.set_option("tb_packed", packed)
+        rb._lib.set_option("tb_uniform", uniform)
         best = None
         for rep in range(3):
             data.set_state(s["qpos"], s["qvel"])
@@ -41,7 +42,8 @@ for dtype, tag in ((torch.float64, "fp64"), (torch.float32, "fp32")):
             ref = data.state.clone()
         else:
             same = bool(torch.equal(ref, data.state))
-        print(json.dumps({"dtype": tag, "tb_minb": minb, "tb_packed": packed, "launch_ms": [round(m, 3) for m in best],
+        print(json.dumps({"dtype": tag, "tb_minb": minb, "tb_packed": packed, "tb_uniform": uniform, "launch_ms": [round(m, 3) for m in best],
                           "env_substeps_per_s_2048": E * K * L / (sum(best) * 1e-3), "state_bitwise_equal_to_first_variant": same}), flush=True)
 rb._lib.set_option("tb_minb", 0)
 rb._lib.set_option("tb_packed", 0)
+rb._lib.set_option("tb_uniform", 1)

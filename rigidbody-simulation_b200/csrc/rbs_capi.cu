@@ -56,6 +56,7 @@ Option g_options[] = {
     {"box_minb", "RBS_BOX_MINB", {0}, 6},                    // resident CTAs per SM of the plane-frame box kernel
     {"box_compact", "RBS_BOX_COMPACT", {0}, 0},              // plane-frame box kernel: CTA-level compaction of contacts (measured slower: off)
     {"tb_minb", "RBS_TB_MINB", {0}, 0},                      // resident CTAs per SM of the two-ball fast kernel (5, 6 or 8; 0 = 6 in double, 8 in float)
+    {"tb_uniform", "RBS_TB_UNIFORM", {0}, 1},                // two-ball fast stepper, uniform radius: radius / reach as launch parameters (1) or registers (0)
     {"tb_packed", "RBS_TB_PACKED", {0}, 0},                  // float two-ball fast stepper: packed fp32x2 kernel, two envs per thread (1) or scalar (0: measured equal, fewer ragged waves)
     {"mb_minb", "RBS_MB_MINB", {0}, 0},                      // resident CTAs per SM of the multi-body stepper (1, 2, 3; 0 = tuned)
     {"ms_skin_percent", "RBS_MS_SKIN_PERCENT", {0}, 50},     // starting skin of the adaptive partner lists
@@ -405,6 +406,8 @@ template <typename T> rbs::TwoBallParams<T> make_params(const rbs_two_ball_args 
     p.fric = (T)a->friction;
     for (int i = 0; i < 3; ++i) p.gdt[i] = p.g[i] * p.dt;
     p.neg1pe = -((T)1 + p.rest);
+    p.reach_u = std::fma((T)2, p.radius_u, (T)0.01);     // the device expressions of step_two_ball_fast_kernel, in T
+    p.reach2_u = (p.reach_u * p.reach_u) * (T)1.0001;
     p.n_ground = a->n_ground_hits ? a->n_ground_hits + w.off : nullptr;
     p.n_pair = a->n_pair_hits ? a->n_pair_hits + w.off : nullptr;
     return p;
@@ -622,13 +625,16 @@ int launch_two_ball_any(const rbs_two_ball_args *a, const Window &w) {
         const bool gz = a->gravity[0] == 0.0 && a->gravity[1] == 0.0;
         // resident CTAs per SM (register cap 64 / 80 / 96); spins and per-ball constants live in shared memory
         int minb = (int)option("tb_minb");
-        if (minb == 0) minb = a->dtype == RBS_F64 ? 6 : 8;     // measured on B200, 1M envs: profiles/r2_ab_two_ball.jsonl
-#define RBS_TB(T, GZ, MINB)                                                                                              \
+        if (minb == 0) minb = (a->dtype == RBS_F64 && (a->radius != nullptr || option("tb_uniform") == 0)) ? 6 : 8;   // measured on B200, 1M envs: profiles/r2_ab_two_ball.jsonl, r2_ab_two_ball_uniform_radius.jsonl
+#define RBS_TB_UR(T, GZ, MINB, UR)                                                                                       \
     do {                                                                                                                 \
-        cudaFuncSetAttribute(rbs::step_two_ball_fast_kernel<T, GZ, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+        cudaFuncSetAttribute(rbs::step_two_ball_fast_kernel<T, GZ, MINB, UR>, cudaFuncAttributePreferredSharedMemoryCarveout, \
                              cudaSharedmemCarveoutMaxShared);                                                            \
-        rbs::step_two_ball_fast_kernel<T, GZ, MINB><<<grid, rbs::kBlock, 0, st>>>(make_params<T>(a, w));                    \
+        rbs::step_two_ball_fast_kernel<T, GZ, MINB, UR><<<grid, rbs::kBlock, 0, st>>>(make_params<T>(a, w));                \
     } while (0)
+        // uniform radius (no per-environment array): radius / reach / reach^2 as launch parameters (option tb_uniform = 0 keeps registers)
+        const bool ur = a->radius == nullptr && option("tb_uniform") != 0;
+#define RBS_TB(T, GZ, MINB) do { if (ur) RBS_TB_UR(T, GZ, MINB, true); else RBS_TB_UR(T, GZ, MINB, false); } while (0)
 #define RBS_TB_MINB(T, GZ) do { if (minb >= 8) RBS_TB(T, GZ, 8); else if (minb >= 6) RBS_TB(T, GZ, 6); else RBS_TB(T, GZ, 5); } while (0)
 #define RBS_TB2(GZ, MINB)                                                                                                \
     do {                                                                                                                 \
@@ -647,6 +653,7 @@ int launch_two_ball_any(const rbs_two_ball_args *a, const Window &w) {
 #undef RBS_TB2
 #undef RBS_TB_MINB
 #undef RBS_TB
+#undef RBS_TB_UR
     } else {
         // strict policy: resident CTAs per SM (option strict_tb_minb: 3 = uncapped, 4 = 128 registers, 5 = 96; 0 = measured best)
         int minb = (int)option("strict_tb_minb");
