@@ -552,6 +552,22 @@ def b200_arm(args):
                "value": world * E * S / (ms / 2 * 1e-3), "unit": METRIC, "body_substeps_per_s": world * E * B * S / (ms / 2 * 1e-3),
                "contacts_per_body_substep": float(calls.sum()) / (3.0 * E * B * S), "impulses_per_body_substep": float(imps.sum()) / (3.0 * E * B * S),
                "kernel": "step_multi_body_kernel"}
+        # end to end through the host-buffer C-ABI call (pinned reference-layout arrays, H2D + S substeps + D2H inside)
+        data.state.copy_(s0)
+        qp0, qv0 = data.qpos.torch().cpu().pin_memory(), data.qvel.torch().cpu().pin_memory()
+        qp_h, qv_h = qp0.clone().pin_memory(), qv0.clone().pin_memory()
+
+        def e2e_reset():
+            qp_h.copy_(qp0)
+            qv_h.copy_(qv0)
+
+        def e2e_step():
+            stepper.run_multi_body_host(model, qp_h, qv_h, S, dt=mixed_pile.timestep, restitution=mixed_pile.restitution_coefficient,
+                                        friction=mixed_pile.friction_coefficient, substeps=F)
+        e_ms, _, _ = timed(e2e_step, 2, 1, before=e2e_reset)
+        nbytes = E * B * 13 * (8 if tdtype == torch.float64 else 4)
+        out["e2e"] = {"value": world * E * S / (e_ms / 2 * 1e-3), "unit": METRIC, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                      "ms_per_step": e_ms / 2, "call": "rbs_run_multi_body_host via stepper.run_multi_body_host (pinned host qpos/qvel)"}
         if rank == 0 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import c_oracle as co

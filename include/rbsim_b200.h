@@ -259,6 +259,7 @@ RBS_API int rbs_reset_envs(int dtype, long n_env, int n_body, int body_fastest, 
 RBS_API int rbs_run_body_plane_host(const rbs_body_plane_args *a, void *qpos_host, void *qvel_host, long total_steps);
 RBS_API int rbs_run_two_ball_host(const rbs_two_ball_args *a, void *qpos_host, void *qvel_host, long total_steps);
 RBS_API int rbs_run_multi_sphere_host(const rbs_multi_sphere_args *a, void *qpos_host, void *qvel_host, long total_steps);
+RBS_API int rbs_run_multi_body_host(const rbs_multi_body_args *a, void *qpos_host, void *qvel_host, long total_steps);
 /* frees the cached device workspace of the host-buffer drivers */
 RBS_API int rbs_release_workspace(void);
 

@@ -115,6 +115,7 @@ PROTOTYPES = {
     "rbs_run_body_plane_host": (c_int, [POINTER(BodyPlaneArgs), c_void_p, c_void_p, c_long]),
     "rbs_run_two_ball_host": (c_int, [POINTER(TwoBallArgs), c_void_p, c_void_p, c_long]),
     "rbs_run_multi_sphere_host": (c_int, [POINTER(MultiSphereArgs), c_void_p, c_void_p, c_long]),
+    "rbs_run_multi_body_host": (c_int, [POINTER(MultiBodyArgs), c_void_p, c_void_p, c_long]),
     "rbs_release_workspace": (c_int, []),
     "rbs_stats": (c_int, [c_int, c_long, c_void_p, c_long, c_void_p, c_double, c_void_p, c_long, POINTER(c_double),
                           POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p]),

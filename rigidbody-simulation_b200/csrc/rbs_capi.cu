@@ -575,16 +575,18 @@ template <typename T> int launch_multi_sphere(const rbs_multi_sphere_args *a, co
     return RBS_OK;
 }
 
-template <typename T> int launch_multi_body(const rbs_multi_body_args *a) {
+inline Window whole(const rbs_multi_body_args *a) { return {0, a->n_env, a->state, a->stride, as_stream(a->stream)}; }
+
+template <typename T> int launch_multi_body(const rbs_multi_body_args *a, const Window &w) {
     rbs::MultiBodyParams<T> p;
     const int B = a->n_body;
-    p.n_env = a->n_env;
-    p.stride = a->stride;
+    p.n_env = w.cnt;
+    p.stride = w.stride;
     p.substeps = a->substeps;
     p.n_body = B;
     p.env_per_block = 256 / B;
     p.has_offset = a->has_offset;
-    p.state = static_cast<T *>(a->state);
+    p.state = static_cast<T *>(w.state);
     p.table = static_cast<const T *>(a->body_table);
     for (int i = 0; i < 3; ++i) {
         p.pp[i] = (T)a->plane_point[i];
@@ -594,8 +596,8 @@ template <typename T> int launch_multi_body(const rbs_multi_body_args *a) {
     p.dt = (T)a->dt;
     p.rest = (T)a->restitution;
     p.fric = (T)a->friction;
-    p.n_contacts = a->n_contacts;
-    p.n_impulses = a->n_impulses;
+    p.n_contacts = a->n_contacts ? a->n_contacts + w.off * B : nullptr;    // counters are indexed env * n_body + body
+    p.n_impulses = a->n_impulses ? a->n_impulses + w.off * B : nullptr;
     const int threads = ((p.env_per_block * B + 31) / 32) * 32;
     const size_t smem = ((size_t)B * rbs::kBodyTable + 2 * (size_t)p.env_per_block * B * 12) * sizeof(T);
     // resident CTAs per SM (option mb_minb: 1 = uncapped registers, 2 = 128, 3 = 80; 0 = tuned default)
@@ -608,13 +610,32 @@ template <typename T> int launch_multi_body(const rbs_multi_body_args *a) {
             if (e__ != cudaSuccess)                                                                                        \
                 return fail(RBS_ECUDA, "rbs_step_multi_body: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e__)); \
         }                                                                                                                  \
-        KERNEL<<<blocks_for(a->n_env, p.env_per_block), threads, smem, as_stream(a->stream)>>>(p);                          \
+        KERNEL<<<blocks_for(w.cnt, p.env_per_block), threads, smem, w.stream>>>(p);                                        \
     } while (0)
     if (minb >= 3) RBS_MB_LAUNCH((rbs::step_multi_body_kernel<T, 256, 3>));
     else if (minb == 2) RBS_MB_LAUNCH((rbs::step_multi_body_kernel<T, 256, 2>));
     else RBS_MB_LAUNCH((rbs::step_multi_body_kernel<T, 256, 1>));
 #undef RBS_MB_LAUNCH
     return check_launch("rbs_step_multi_body");
+}
+
+int validate_multi_body(const rbs_multi_body_args *a, bool need_state) {
+    if (!a) return fail(RBS_EINVAL, "rbs_step_multi_body: null args");
+    if (bad_dtype(a->dtype)) return fail(RBS_EINVAL, "rbs_step_multi_body: dtype %d is not RBS_F32/RBS_F64", a->dtype);
+    if (a->n_body < 1 || a->n_body > 256) return fail(RBS_EINVAL, "rbs_step_multi_body: n_body %d outside 1..256", a->n_body);
+    if (a->n_env < 0) return fail(RBS_EINVAL, "rbs_step_multi_body: n_env %ld < 0", a->n_env);
+    if (a->substeps < 1) return fail(RBS_EINVAL, "rbs_step_multi_body: substeps %d < 1", a->substeps);
+    if (!a->body_table) return fail(RBS_EINVAL, "rbs_step_multi_body: null body_table");
+    if (need_state) {
+        if (a->n_env > 0 && !a->state) return fail(RBS_EINVAL, "rbs_step_multi_body: null state");
+        if (a->stride < a->n_env * a->n_body)
+            return fail(RBS_EINVAL, "rbs_step_multi_body: stride %ld < n_env*n_body %ld", a->stride, a->n_env * a->n_body);
+    }
+    return RBS_OK;
+}
+
+int launch_multi_body_any(const rbs_multi_body_args *a, const Window &w) {
+    return a->dtype == RBS_F64 ? launch_multi_body<double>(a, w) : launch_multi_body<float>(a, w);
 }
 
 int launch_two_ball_any(const rbs_two_ball_args *a, const Window &w) {
@@ -1010,17 +1031,10 @@ int rbs_step_multi_sphere(const rbs_multi_sphere_args *a) {
 }
 
 int rbs_step_multi_body(const rbs_multi_body_args *a) {
-    if (!a) return fail(RBS_EINVAL, "rbs_step_multi_body: null args");
-    if (bad_dtype(a->dtype)) return fail(RBS_EINVAL, "rbs_step_multi_body: dtype %d is not RBS_F32/RBS_F64", a->dtype);
-    if (a->n_body < 1 || a->n_body > 256) return fail(RBS_EINVAL, "rbs_step_multi_body: n_body %d outside 1..256", a->n_body);
-    if (a->n_env < 0) return fail(RBS_EINVAL, "rbs_step_multi_body: n_env %ld < 0", a->n_env);
-    if (a->substeps < 1) return fail(RBS_EINVAL, "rbs_step_multi_body: substeps %d < 1", a->substeps);
-    if (!a->body_table) return fail(RBS_EINVAL, "rbs_step_multi_body: null body_table");
-    if (a->n_env > 0 && !a->state) return fail(RBS_EINVAL, "rbs_step_multi_body: null state");
-    if (a->stride < a->n_env * a->n_body)
-        return fail(RBS_EINVAL, "rbs_step_multi_body: stride %ld < n_env*n_body %ld", a->stride, a->n_env * a->n_body);
+    int rc = validate_multi_body(a, true);
+    if (rc) return rc;
     if (a->n_env == 0) return RBS_OK;
-    return a->dtype == RBS_F64 ? launch_multi_body<double>(a) : launch_multi_body<float>(a);
+    return launch_multi_body_any(a, whole(a));
 }
 
 int rbs_pack_state(int dtype, long n_env, int n_body, int body_fastest, const void *qpos, const void *qvel,
@@ -1092,6 +1106,13 @@ int rbs_run_multi_sphere_host(const rbs_multi_sphere_args *a, void *qpos_host, v
     // one wave = the CTAs resident at once (about five 128-thread CTAs per SM), in environments
     const long resident = threads <= 256 ? 5 : (threads <= 512 ? 2 : 1);
     return run_host_pipelined(a, a->n_body, 1, resident * epb, qpos_host, qvel_host, total_steps, launch_multi_sphere_any);
+}
+
+int rbs_run_multi_body_host(const rbs_multi_body_args *a, void *qpos_host, void *qvel_host, long total_steps) {
+    int rc = validate_multi_body(a, false);
+    if (rc) return rc;
+    // one wave = two resident 256-thread CTAs per SM, in environments
+    return run_host_pipelined(a, a->n_body, 1, 2L * (256 / a->n_body), qpos_host, qvel_host, total_steps, launch_multi_body_any);
 }
 
 int rbs_release_workspace(void) {

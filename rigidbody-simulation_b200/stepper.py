@@ -419,6 +419,16 @@ def run_multi_sphere_host(model, qpos, qvel, total_steps, dt=None, restitution=1
                                                      _host_ptr(qvel, model.dtype, (E, 6 * B)), int(total_steps)))
 
 
+def run_multi_body_host(model, qpos, qvel, total_steps, dt=None, restitution=0.2, friction=0.6, substeps=8):
+    """Advance host arrays qpos[E, 7B], qvel[E, 6B] (in place) by ``total_steps`` steps of the multi-body stepper (N4)."""
+    data = _HostShim(model, model.nfree, layout="body")
+    a = multi_body_args(model, data, model.opt.timestep if dt is None else dt, restitution, friction, substeps, count=False)
+    a.stream = current_stream(model.device)
+    E, B = model.nenv, model.nfree
+    _lib.check(_lib.load().rbs_run_multi_body_host(ctypes.byref(a), _host_ptr(qpos, model.dtype, (E, 7 * B)),
+                                                   _host_ptr(qvel, model.dtype, (E, 6 * B)), int(total_steps)))
+
+
 class _HostShim:
     """Carries the sizes the *_args builders read from a BatchedData; the host drivers use the library's own
     device workspace, so no state tensor exists on the Python side."""

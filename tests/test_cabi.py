@@ -16,7 +16,7 @@ def declared_symbols():
 def test_header_and_binding_agree():
     from rigidbody_simulation_b200 import _lib
     assert declared_symbols() == sorted(_lib.PROTOTYPES)
-    assert len(declared_symbols()) == 24
+    assert len(declared_symbols()) == 25
 
 
 def test_library_exports_every_declared_symbol():

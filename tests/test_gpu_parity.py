@@ -1590,3 +1590,21 @@ def test_multi_body_shapes_vs_oracle(rb, B, E):
     assert cnt[0].sum() > 0
     with pytest.raises(ValueError):
         stepper.step_multi_body(model, data, 0.005, 0.2, 0.6, substeps=0)
+
+
+def test_multi_body_host_buffer_driver_matches_device_path(rb):
+    """rbs_run_multi_body_host (reference-layout host arrays in and out, chunk pipeline inside) computes what the
+    device-resident stepper computes, bit for bit, on a batch large enough for several pipeline chunks and an odd tail."""
+    import rigidbody_simulation_b200.mj as mj
+    from rigidbody_simulation_b200 import scenes, stepper, synth
+    E, B = 40_003, len(MIXED_BODIES)
+    model, data, _, _, _ = _multi_body_case(MIXED_BODIES, E, np.float64, pitch=0.8)
+    s = synth.multi_body(E, MIXED_BODIES, pitch=0.8)
+    qp, qv = s["qpos"].copy(), s["qvel"].copy()
+    stepper.run_multi_body_host(model, qp, qv, 150, dt=0.005, restitution=0.2, friction=0.6, substeps=64)
+    for k in (64, 64, 22):
+        stepper.step_multi_body(model, data, 0.005, 0.2, 0.6, substeps=k)
+    gq, gv = state_of(data)
+    assert np.array_equal(gq, qp) and np.array_equal(gv, qv)
+    with pytest.raises(ValueError):
+        stepper.run_multi_body_host(model, qp[:10], qv, 1)
