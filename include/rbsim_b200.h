@@ -202,8 +202,8 @@ RBS_API int rbs_step_multi_sphere(const rbs_multi_sphere_args *a);
  * only ever meet plane-sphere, plane-box and sphere-sphere contacts).  The step is the loop rbs_step_multi_sphere
  * replaces (src/simulation/multi_sphere_bounce.py:42-92, repaired), body by body with the reference's impulse
  * (src/physics/collision.py:7-48), its application (src/physics/physics_utils.py:25-49) and the literal world inertia
- * (collision.py:51-53) per contact, strict arithmetic; the contact set adds sphere-box and box-box (vertex-face)
- * pairs, geom1 = the lower body index, normal geom1 -> geom2, never flipped (DESIGN.md "N4").
+ * (collision.py:51-53) per contact, strict arithmetic; the contact set adds sphere-box and box-box (vertices inside
+ * the other box, edges passing through it) pairs, geom1 = the lower body index, normal geom1 -> geom2, never flipped (DESIGN.md "N4").
  * body_table: DEVICE array [n_body][RBS_BODY_TABLE_WIDTH] of dtype, shared by every environment; per body
  *   [0] geom type (0 sphere, 1 box)   [1..3] size (radius,-,- | half extents)   [4] mass   [5..7] principal inertia
  *   [8..10] geom position and [11..14] geom quaternion (wxyz) in the body frame (read only when has_offset != 0)

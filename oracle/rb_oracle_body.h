@@ -350,7 +350,8 @@ void SUF(rbo_step_multi_sphere)(long E, int B, int steps, REAL *qpos, REAL *qvel
  * reference's A1 / A2 / A4 per contact; the CONTACT SET is widened by the two pair functions below, which are this
  * project's own specification (DESIGN.md "N4"), written in the conventions of Appendix A.2 -- contact = {dist, pos midway
  * between the two surfaces, normal from geom1 to geom2}.  Parity of these two against MuJoCo's mjc_SphereBox /
- * mjc_BoxBox is NOT claimed (box-box here has vertex-face contacts only, no edge-edge).
+ * mjc_BoxBox is NOT claimed (box-box here: vertices inside the other box, then edges passing through it; no SAT, no
+ * clipped face polygons).
  * Geoms may sit at an offset in their body's frame (gpos, gquat: N1 remainder); the impulse arm is still taken from the
  * body origin qpos[:3], as the reference does (collision.py:75).
  * ------------------------------------------------------------------------------------------------ */
@@ -414,23 +415,72 @@ static int SUF(sphere_box)(const REAL *cs, REAL rad, const REAL *cb, const REAL 
     return 1;
 }
 
-/* vertices of box V (centre cv, rotation Rv, half extents hv; index order, bit0->x bit1->y bit2->z) that lie inside box F:
- * each leaves F through its nearest face.  sign = +1 when F is geom1 (the face normal already points geom1 -> geom2),
- * -1 when F is geom2.  Appends to out[], at most `room` contacts. */
-static int SUF(box_vertices_in_box)(const REAL *cv, const REAL *Rv, const REAL *hv, const REAL *cf, const REAL *Rf,
-                                    const REAL *hf, REAL sign, SUF(contact_t) *out, int room) {
-    int cnt = 0;
-    for (int i = 0; i < 8 && cnt < room; ++i) {
+/* Features of box V (centre cv, rotation Rv, half extents hv) inside box F: first its vertices (index order, bit0->x
+ * bit1->y bit2->z) that lie inside F, then its edges that pass through F without either end point inside it and without
+ * both end points beyond one face of F -- the edge is clipped against F's three slabs in F's frame and the middle of the
+ * clipped piece is taken (covers edge-edge crossings and an edge lying across a face: crossed planks).  Every such point
+ * of V leaves F through F's nearest face.  sign = +1 when F is geom1 (the face normal already points geom1 -> geom2),
+ * -1 when F is geom2.  Edge e = 4*a + c: along axis a of V, c = the signs of the other two axes (lower axis in bit 0).
+ * Appends to out[], at most `room` contacts. */
+static int SUF(box_features_in_box)(const REAL *cv, const REAL *Rv, const REAL *hv, const REAL *cf, const REAL *Rf,
+                                    const REAL *hf, REAL sign, SUF(contact_t) *out, int room, int phase, REAL (*l)[3],
+                                    int *inside_io) {
+    /* phase 0: the vertex pass (fills l[8][3] = V's vertices in F's frame and the mask of those inside F);
+     * phase 1: the edge pass (reads both) */
+    int cnt = 0, inside = phase ? *inside_io : 0;
+    for (int i = 0; i < 8 && phase == 0; ++i) {
         REAL v[3] = {(i & 1) ? hv[0] : -hv[0], (i & 2) ? hv[1] : -hv[1], (i & 4) ? hv[2] : -hv[2]};
-        REAL corner[3], x[3], l[3];
+        REAL corner[3], x[3];
         SUF(matvec3)(Rv, v, corner);
         for (int k = 0; k < 3; ++k) x[k] = cv[k] + corner[k];
-        SUF(to_box_frame)(cf, Rf, x, l);
+        SUF(to_box_frame)(cf, Rf, x, l[i]);
         int ax = 0;
-        REAL depth = hf[0] - SUF(absr)(l[0]);
-        for (int k = 1; k < 3; ++k) { REAL dk = hf[k] - SUF(absr)(l[k]); if (dk < depth) { depth = dk; ax = k; } }
+        REAL depth = hf[0] - SUF(absr)(l[i][0]);
+        for (int k = 1; k < 3; ++k) { REAL dk = hf[k] - SUF(absr)(l[i][k]); if (dk < depth) { depth = dk; ax = k; } }
         if (!(depth > 0)) continue;                       /* outside F (or on its surface) */
-        REAL sg = l[ax] >= 0 ? (REAL)1 : (REAL)-1;        /* outward normal of the nearest face: sg * axis ax of F */
+        inside |= 1 << i;
+        if (cnt >= room) continue;
+        REAL sg = l[i][ax] >= 0 ? (REAL)1 : (REAL)-1;     /* outward normal of the nearest face: sg * axis ax of F */
+        REAL m[3] = {sg * Rf[ax], sg * Rf[3 + ax], sg * Rf[6 + ax]};
+        REAL hd = (REAL)0.5 * depth;
+        for (int k = 0; k < 3; ++k) { out[cnt].pos[k] = x[k] + m[k] * hd; out[cnt].n[k] = sign * m[k]; }
+        out[cnt].dist = -depth;
+        ++cnt;
+    }
+    if (phase == 0) { *inside_io = inside; return cnt; }
+    for (int e = 0; e < 12 && cnt < room; ++e) {
+        int a = e >> 2, b1 = a == 0 ? 1 : 0, b2 = a == 2 ? 1 : 2;
+        int i0 = ((e & 1) ? 1 << b1 : 0) | ((e & 2) ? 1 << b2 : 0), i1 = i0 | (1 << a);
+        if (inside & ((1 << i0) | (1 << i1))) continue;   /* an end point inside F: a vertex contact already */
+        const REAL *p0 = l[i0], *p1 = l[i1];
+        int beyond = 0;
+        for (int k = 0; k < 3; ++k)
+            if ((p0[k] >= hf[k] && p1[k] >= hf[k]) || (p0[k] <= -hf[k] && p1[k] <= -hf[k])) beyond = 1;
+        if (beyond) continue;                             /* both ends beyond one face: the edge cannot enter F */
+        REAL t0 = 0, t1 = 1, d[3];
+        int empty = 0;
+        for (int k = 0; k < 3; ++k) {
+            d[k] = p1[k] - p0[k];
+            if (d[k] == 0) { if (!(hf[k] - SUF(absr)(p0[k]) > 0)) empty = 1; continue; }
+            REAL ta = (-hf[k] - p0[k]) / d[k], tb = (hf[k] - p0[k]) / d[k];
+            REAL lo = ta < tb ? ta : tb, hi = ta < tb ? tb : ta;
+            if (lo > t0) t0 = lo;
+            if (hi < t1) t1 = hi;
+        }
+        if (empty || !(t0 < t1)) continue;
+        REAL tm = (REAL)0.5 * (t0 + t1), lm[3];
+        for (int k = 0; k < 3; ++k) lm[k] = p0[k] + d[k] * tm;
+        int ax = 0;
+        REAL depth = hf[0] - SUF(absr)(lm[0]);
+        for (int k = 1; k < 3; ++k) { REAL dk = hf[k] - SUF(absr)(lm[k]); if (dk < depth) { depth = dk; ax = k; } }
+        if (!(depth > 0)) continue;
+        REAL v0[3] = {(i0 & 1) ? hv[0] : -hv[0], (i0 & 2) ? hv[1] : -hv[1], (i0 & 4) ? hv[2] : -hv[2]};
+        REAL v1[3] = {(i1 & 1) ? hv[0] : -hv[0], (i1 & 2) ? hv[1] : -hv[1], (i1 & 4) ? hv[2] : -hv[2]};
+        REAL w0[3], w1[3], x[3];
+        SUF(matvec3)(Rv, v0, w0);
+        SUF(matvec3)(Rv, v1, w1);
+        for (int k = 0; k < 3; ++k) { REAL x0 = cv[k] + w0[k], x1 = cv[k] + w1[k]; x[k] = x0 + (x1 - x0) * tm; }
+        REAL sg = lm[ax] >= 0 ? (REAL)1 : (REAL)-1;
         REAL m[3] = {sg * Rf[ax], sg * Rf[3 + ax], sg * Rf[6 + ax]};
         REAL hd = (REAL)0.5 * depth;
         for (int k = 0; k < 3; ++k) { out[cnt].pos[k] = x[k] + m[k] * hd; out[cnt].n[k] = sign * m[k]; }
@@ -440,12 +490,31 @@ static int SUF(box_vertices_in_box)(const REAL *cv, const REAL *Rv, const REAL *
     return cnt;
 }
 
-/* box (geom1 = lower id) - box (geom2): vertices of geom2 inside geom1, then vertices of geom1 inside geom2; <= 8 */
+/* box (geom1 = lower id) - box (geom2): nothing when a face normal of either box separates them; else the vertices of
+ * geom2 inside geom1, the vertices of geom1 inside geom2 (<= 8), and, while the pair has fewer than four contacts, the
+ * edges of geom2 through geom1 and then the edges of geom1 through geom2 */
 static int SUF(box_box)(const REAL *c1, const REAL *R1, const REAL *h1, const REAL *c2, const REAL *R2, const REAL *h2,
                         SUF(contact_t) *out) {
-    int cnt = SUF(box_vertices_in_box)(c2, R2, h2, c1, R1, h1, (REAL)1, out, 8);
-    cnt += SUF(box_vertices_in_box)(c1, R1, h1, c2, R2, h2, (REAL)-1, out + cnt, 8 - cnt);
-    return cnt;
+    /* separating-axis test on the six face normals first: boxes apart along one of them have no contact */
+    REAL t[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]}, C[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C[3 * i + j] = SUF(absr)((R1[i] * R2[j] + R1[3 + i] * R2[3 + j]) + R1[6 + i] * R2[6 + j]);
+    for (int i = 0; i < 3; ++i) {
+        REAL d1 = SUF(absr)((t[0] * R1[i] + t[1] * R1[3 + i]) + t[2] * R1[6 + i]);
+        REAL d2 = SUF(absr)((t[0] * R2[i] + t[1] * R2[3 + i]) + t[2] * R2[6 + i]);
+        if (d1 > h1[i] + ((h2[0] * C[3 * i] + h2[1] * C[3 * i + 1]) + h2[2] * C[3 * i + 2])) return 0;
+        if (d2 > h2[i] + ((h1[0] * C[i] + h1[1] * C[3 + i]) + h1[2] * C[6 + i])) return 0;
+    }
+    REAL l21[8][3], l12[8][3];
+    int in21 = 0, in12 = 0;
+    int cnt = SUF(box_features_in_box)(c2, R2, h2, c1, R1, h1, (REAL)1, out, 8, 0, l21, &in21);
+    cnt += SUF(box_features_in_box)(c1, R1, h1, c2, R2, h2, (REAL)-1, out + cnt, 8 - cnt, 0, l12, &in12);
+    /* edge contacts only fill a pair up to four contacts: a pair that already rests on three or four vertices has its
+     * support, and most touching pairs of a settled pile are of that kind */
+    int room = cnt < 4 ? 4 - cnt : 0;
+    int ne = SUF(box_features_in_box)(c2, R2, h2, c1, R1, h1, (REAL)1, out + cnt, room, 1, l21, &in21);
+    ne += SUF(box_features_in_box)(c1, R1, h1, c2, R2, h2, (REAL)-1, out + cnt + ne, room - ne, 1, l12, &in12);
+    return cnt + ne;
 }
 
 /* world pose of a body's geom: centre and rotation matrix (mju_quat2Mat of the normalised quaternion) */

@@ -1608,3 +1608,33 @@ def test_multi_body_host_buffer_driver_matches_device_path(rb):
     assert np.array_equal(gq, qp) and np.array_equal(gv, qv)
     with pytest.raises(ValueError):
         stepper.run_multi_body_host(model, qp[:10], qv, 1)
+
+
+def test_multi_body_box_edges_through_boxes(rb):
+    """Box pairs that touch without any vertex of one inside the other -- planks crossed at random angles, one dropped on
+    the other -- are held by the edge-through-box contacts: bit for bit the oracle, the upper plank ends on the lower one
+    (without those contacts it falls through to the ground)."""
+    import rigidbody_simulation_b200.mj as mj
+    from rigidbody_simulation_b200 import scenes, stepper, synth
+    E, B = 1500, 2
+    planks = [{"type": "box", "size": [1.0, 0.2, 0.15]}, {"type": "box", "size": [0.2, 1.0, 0.15]}]
+    model = mj.MjModel.from_xml_string(scenes.multi_body_xml(planks, density=200.0), nenv=E, dtype=torch.float64)
+    data = mj.MjData(model, layout="body")
+    f = synth._Fields(synth.SEED, 0, E, 950)
+    qpos = np.zeros((E, B, 7)); qvel = np.zeros((E, B, 6))
+    qpos[:, 0, :3] = [0, 0, 0.15]; qpos[:, 0, 3] = 1
+    yaw = f.u(-0.6, 0.6)
+    qpos[:, 1, 0] = f.u(-0.1, 0.1); qpos[:, 1, 1] = f.u(-0.1, 0.1); qpos[:, 1, 2] = f.u(0.5, 0.9)
+    qpos[:, 1, 3] = np.cos(yaw / 2); qpos[:, 1, 6] = np.sin(yaw / 2)
+    data.set_state(qpos.reshape(E, -1), qvel.reshape(E, -1))
+    tab = stepper.body_table(model)
+    cnt = (np.zeros((E, B), np.uint32), np.zeros((E, B), np.uint32))
+    qp, qv = qpos.copy(), qvel.copy()
+    co.step_multi_body(qp, qv, 300, gtype=tab[:, 0].astype(np.int32), mass=tab[:, 4], inertia=tab[:, 5:8], size=tab[:, 1:4],
+                       plane_pos=[0, 0, 0], plane_normal=[0, 0, 1], gravity=G, dt=0.005, restitution=0.2, friction=0.6, counters=cnt)
+    stepper.step_multi_body(model, data, 0.005, 0.2, 0.6, substeps=300)
+    gq, gv = state_of(data)
+    assert np.array_equal(gq, qp.reshape(E, -1)) and np.array_equal(gv, qv.reshape(E, -1))
+    calls, imps = data.counters()
+    assert np.array_equal(calls, cnt[0]) and np.array_equal(imps, cnt[1])
+    assert (qp[:, 1, 2] > 0.3 + 0.15 - 0.06).mean() > 0.95, (qp[:, 1, 2] > 0.39).mean()     # resting on the lower plank (top face at 0.3)
