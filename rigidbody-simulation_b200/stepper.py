@@ -341,12 +341,15 @@ def multi_body_args(model, data, dt, restitution, friction, substeps, count=True
         raise ValueError("scene has no plane geom")
     if data.nfree > 256:
         raise ValueError("the multi-body step handles at most 256 bodies per environment")
-    host = body_table(model)                       # re-read every call: model.body_mass[...] = ... between steps takes effect
+    # The table is rebuilt (and re-uploaded) only when the model's mass / inertia arrays have changed since the last call:
+    # model.body_mass[...] = ... between steps takes effect, a per-frame loop does not pay O(bodies) of Python per step.
     cached = getattr(model, "_body_table_cache", None)
-    if cached is None or not np.array_equal(cached[0], host):
-        cached = (host, torch.as_tensor(host, dtype=model.dtype).to(model.device).contiguous())
+    if cached is None or not (np.array_equal(cached[0], model.body_mass) and np.array_equal(cached[1], model.body_inertia)):
+        host = body_table(model)
+        cached = (model.body_mass.copy(), model.body_inertia.copy(),
+                  torch.as_tensor(host, dtype=model.dtype).to(model.device).contiguous())
         model._body_table_cache = cached
-    cache = cached[1]
+    cache = cached[2]
     a = _lib.MultiBodyArgs()
     a.dtype, a.substeps, a.n_body = rbs_dtype(model.dtype), int(substeps), data.nfree
     a.has_offset = int(model.has_offset_geoms)

@@ -1638,3 +1638,25 @@ def test_multi_body_box_edges_through_boxes(rb):
     calls, imps = data.counters()
     assert np.array_equal(calls, cnt[0]) and np.array_equal(imps, cnt[1])
     assert (qp[:, 1, 2] > 0.3 + 0.15 - 0.06).mean() > 0.95, (qp[:, 1, 2] > 0.39).mean()     # resting on the lower plank (top face at 0.3)
+
+
+def test_multi_body_follows_model_edits(rb):
+    """The cached body table is rebuilt when the model's mass / inertia arrays are edited between steps (MuJoCo-style):
+    the second half of a run with a doubled mass of body 1 equals a fresh scene built with that mass."""
+    import rigidbody_simulation_b200.mj as mj
+    from rigidbody_simulation_b200 import scenes, stepper, synth
+    E = 512
+    model, data, _, _, _ = _multi_body_case(MIXED_BODIES, E, np.float64)
+    stepper.step_multi_body(model, data, 0.005, 0.2, 0.6, substeps=40)
+    half = data.state.clone()
+    model.body_mass[model.free_ids[0]] *= 2.0
+    stepper.step_multi_body(model, data, 0.005, 0.2, 0.6, substeps=40)
+    model2, data2, _, _, _ = _multi_body_case(MIXED_BODIES, E, np.float64)
+    model2.body_mass[model2.free_ids[0]] *= 2.0
+    data2.state.copy_(half)
+    stepper.step_multi_body(model2, data2, 0.005, 0.2, 0.6, substeps=40)
+    assert torch.equal(data.state, data2.state)
+    model3, data3, _, _, _ = _multi_body_case(MIXED_BODIES, E, np.float64)
+    data3.state.copy_(half)
+    stepper.step_multi_body(model3, data3, 0.005, 0.2, 0.6, substeps=40)
+    assert not torch.equal(data.state, data3.state)            # the edit did change the dynamics
