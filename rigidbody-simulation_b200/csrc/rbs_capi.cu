@@ -216,12 +216,37 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
         if constexpr (SCHEME == 0) {
             // the contact path compacted across the CTA (bit-identical results; strict_compact = 0 keeps one environment's
             // whole substep in its own thread).  Not with an applied wrench: then every lane builds the inverse anyway.
-            // Option strict_compact: -1 = never, 4 / 5 = always (at 4 / 5 resident CTAs per SM), 0 = where it measured faster
-            // (profiles/r2_ab_strict.jsonl: sphere 2.28e10 -> 2.56e10 at 5 CTAs; cube 1.02e10 -> 7.7e9, so not for boxes: with
-            // only the hit environments' warps in the ~890-instruction dependent chain, the path turns latency-bound).
+            // Option strict_compact: -1 = never, 4 / 5 = always (at 4 / 5 resident CTAs per SM), 2x-4x = K environments per thread
+            // in registers (measured slower), 5x-8x = K environments per thread RESIDENT IN SHARED MEMORY (uniform mass / size /
+            // inertia), 0 = where it measured faster (profiles/r2_ab_strict.jsonl, r2_ab_strict_resident.jsonl: sphere 2.28e10 ->
+            // 2.56e10 compacted at 5 CTAs -> 3.60e10 resident at K = 3, 4 CTAs; cube 1.02e10 -> 7.7e9 / 1.08e10 / 6.6e9 (incline),
+            // so boxes stay on the thread-per-environment kernel).
             long compact = option("strict_compact");
-            if (compact == 0) compact = GEOM == 0 ? 5 : -1;
-            if (!a->xfrc && compact >= 20) {
+            if (compact == 0) compact = GEOM == 0 ? ((!a->mass && !a->size && !a->inertia) ? 64 : 5) : -1;
+            if (!a->xfrc && compact >= 50 && !a->mass && !a->size && !a->inertia) {
+                // state resident in shared memory, K environments per thread: compact = 50 + 10*(K - 2) + resident CTAs, K = 2..4
+#define RBS_RES(KK, MB)                                                                                                  \
+    do {                                                                                                                 \
+        const size_t smem__ = (size_t)(KK) * rbs::kBlock * (13 * sizeof(T) + 4);                                         \
+        cudaFuncSetAttribute(rbs::step_body_plane_resident_kernel<T, GEOM, KK, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem__); \
+        cudaFuncSetAttribute(rbs::step_body_plane_resident_kernel<T, GEOM, KK, MB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+        rbs::step_body_plane_resident_kernel<T, GEOM, KK, MB><<<blocks_for(w.cnt, (KK) * rbs::kBlock), rbs::kBlock, smem__, st>>>(p); \
+    } while (0)
+                switch (compact) {
+                    case 53: RBS_RES(2, 3); return;
+                    case 63: RBS_RES(3, 3); return;
+                    case 83: RBS_RES(5, 3); return;
+                    case 54: RBS_RES(2, 4); return;
+                    case 55: RBS_RES(2, 5); return;
+                    case 56: RBS_RES(2, 6); return;
+                    case 64: RBS_RES(3, 4); return;
+                    case 65: RBS_RES(3, 5); return;
+                    case 73: RBS_RES(4, 3); return;
+                    default: RBS_RES(4, 4); return;
+                }
+#undef RBS_RES
+            }
+            if (!a->xfrc && compact >= 20 && compact < 50) {
                 // K environments per thread (K * 128 per CTA), all warps work through the contact phase: compact = 10*K + resident CTAs
 #define RBS_CM(KK, MB)                                                                                                   \
     do {                                                                                                                 \
