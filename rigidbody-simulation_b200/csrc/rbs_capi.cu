@@ -232,17 +232,13 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
         cudaFuncSetAttribute(rbs::step_body_plane_resident_kernel<T, GEOM, KK, MB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
         rbs::step_body_plane_resident_kernel<T, GEOM, KK, MB><<<blocks_for(w.cnt, (KK) * rbs::kBlock), rbs::kBlock, smem__, st>>>(p); \
     } while (0)
+                // (the A/B of profiles/r2_ab_strict_resident.jsonl also had K = 2..5 at 3..6 resident CTAs; the instantiations kept
+                // are the best of each K)
                 switch (compact) {
-                    case 53: RBS_RES(2, 3); return;
-                    case 63: RBS_RES(3, 3); return;
-                    case 83: RBS_RES(5, 3); return;
                     case 54: RBS_RES(2, 4); return;
-                    case 55: RBS_RES(2, 5); return;
-                    case 56: RBS_RES(2, 6); return;
-                    case 64: RBS_RES(3, 4); return;
                     case 65: RBS_RES(3, 5); return;
-                    case 73: RBS_RES(4, 3); return;
-                    default: RBS_RES(4, 4); return;
+                    case 74: RBS_RES(4, 4); return;
+                    default: RBS_RES(3, 4); return;
                 }
 #undef RBS_RES
             }
@@ -255,13 +251,9 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
         cudaFuncSetAttribute(rbs::step_body_plane_compact_multi_kernel<T, GEOM, KK, MB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
         rbs::step_body_plane_compact_multi_kernel<T, GEOM, KK, MB><<<blocks_for(w.cnt, (KK) * rbs::kBlock), rbs::kBlock, smem__, st>>>(p); \
     } while (0)
+                // (profiles/r2_ab_strict_multi_env.jsonl measured K = 2..4 at 3..6 resident CTAs, all slower; two are kept as the record)
                 switch (compact) {
-                    case 24: RBS_CM(2, 4); return;
                     case 25: RBS_CM(2, 5); return;
-                    case 26: RBS_CM(2, 6); return;
-                    case 34: RBS_CM(3, 4); return;
-                    case 35: RBS_CM(3, 5); return;
-                    case 43: RBS_CM(4, 3); return;
                     default: RBS_CM(4, 4); return;
                 }
 #undef RBS_CM
