@@ -151,7 +151,7 @@ def _reference_two_ball_namespace():
             import contextlib
             import glfw
             glfw.reset(0, False)
-            with contextlib.redirect_stdout(sys.stderr):     # the script reports its (stubbed) plots and video on stdout
+            with open(os.devnull, "w") as sink, contextlib.redirect_stdout(sink):   # the script reports its (stubbed) plots and video on stdout
                 _TWO_BALL_NS = runpy.run_path(os.path.join(REF_DIR, "simulation", "ball_collision.py"), run_name="__main__")
         finally:
             os.chdir(cwd)
