@@ -1,5 +1,5 @@
 """Timing / ncu target: config 4 (cube on a plane, 1,048,576 envs), fast policy, fp64.
-    python profiles/prof_cube.py [bounce|incline] [substeps per launch]
+    python profiles/prof_cube.py [bounce|incline] [substeps per launch] [fast|strict]
 """
 import os
 import sys
@@ -13,6 +13,7 @@ from rigidbody_simulation_b200 import scenes, stepper, synth
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "bounce"
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+ARITH = sys.argv[3] if len(sys.argv) > 3 else "fast"
 E = 1 << 20
 s = synth.cube(E, kind=kind)
 model = scenes.cube_on_plane(E, theta=s["theta"], device=torch.device("cuda:0"), dtype=torch.float64)
@@ -21,7 +22,7 @@ data.set_state(s["qpos"], s["qvel"])
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
 for i in range(5):
     ev[i].record()
-    stepper.step_body_plane(model, data, -1, s["dt"], 0.2, 0.6, 1e-4, substeps=K, count=(i == 4), arith="fast")
+    stepper.step_body_plane(model, data, -1, s["dt"], 0.2, 0.6, 1e-4, substeps=K, count=(i == 4), arith=ARITH)
 ev[5].record()
 torch.cuda.synchronize()
 ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(5)]
