@@ -225,12 +225,12 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
             if (compact == 0) compact = GEOM == 0 ? ((!a->mass && !a->size && !a->inertia) ? 64 : 5) : -1;
             if (!a->xfrc && compact >= 50 && !a->mass && !a->size && !a->inertia) {
                 // state resident in shared memory, K environments per thread: compact = 50 + 10*(K - 2) + resident CTAs, K = 2..4
-#define RBS_RES(KK, MB, WP)                                                                                              \
+#define RBS_RES(KK, MB, WP, ...)                                                                                              \
     do {                                                                                                                 \
         const size_t smem__ = (size_t)(KK) * rbs::kBlock * (13 * sizeof(T) + 4);                                         \
-        cudaFuncSetAttribute(rbs::step_body_plane_resident_kernel<T, GEOM, KK, MB, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem__); \
-        cudaFuncSetAttribute(rbs::step_body_plane_resident_kernel<T, GEOM, KK, MB, WP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
-        rbs::step_body_plane_resident_kernel<T, GEOM, KK, MB, WP><<<blocks_for(w.cnt, (KK) * rbs::kBlock), rbs::kBlock, smem__, st>>>(p); \
+        cudaFuncSetAttribute(rbs::step_body_plane_resident_kernel<T, GEOM, KK, MB, WP, ##__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem__); \
+        cudaFuncSetAttribute(rbs::step_body_plane_resident_kernel<T, GEOM, KK, MB, WP, ##__VA_ARGS__>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+        rbs::step_body_plane_resident_kernel<T, GEOM, KK, MB, WP, ##__VA_ARGS__><<<blocks_for(w.cnt, (KK) * rbs::kBlock), rbs::kBlock, smem__, st>>>(p); \
     } while (0)
                 // (the A/B of profiles/r2_ab_strict_resident.jsonl also had K = 2..5 at 3..6 resident CTAs; the instantiations kept
                 // are the best of each K).  1KM: the same with one queue per WARP (K environments per lane, M resident CTAs): bit-identical,
@@ -239,6 +239,9 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
                     case 54: RBS_RES(2, 4, false); return;
                     case 65: RBS_RES(3, 5, false); return;
                     case 74: RBS_RES(4, 4, false); return;
+                    case 264: RBS_RES(3, 4, false, true); return;     // 2KM: phases A and C as rolled loops over the K columns (cube bounce:
+                                                                      // 1.56 / 1.63e10 at 264 / 274 against 1.32e10 thread-per-env; incline and sphere slower)
+                    case 274: RBS_RES(4, 4, false, true); return;
                     case 124: RBS_RES(2, 4, true); return;
                     case 134: RBS_RES(3, 4, true); return;
                     case 135: RBS_RES(3, 5, true); return;
