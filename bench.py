@@ -477,16 +477,15 @@ def b200_arm(args):
         other = "strict" if args.arith == "fast" else "fast"
         o_ms, _, _ = timed(lambda: w.step(arith=other), 1 if not headline else max(2, steps // 3), 1, before=w.reset)
         out["other_policies"] = {"unit": METRIC, "values": {other: w.E_job * w.S / (o_ms / (1 if not headline else max(2, steps // 3)) * 1e-3)}}
-        if name == "cube_bounce" and other == "strict":
-            # the resident-in-shared-memory strict stepper (K = 4 environments per thread, rolled column loops) wins where a
-            # minority of the environments touches the plane per substep and loses on the incline, so it is an option, not
-            # the default for boxes (profiles/r2_ab_strict_rolled_resident.jsonl); same bits either way
-            old_opt = rb._lib.set_option("strict_compact", 274)
+        if name in ("cube_bounce", "cube_incline") and other == "strict":
+            # the thread-per-environment strict kernel beside the default (rolled resident kernel with a per-CTA density
+            # vote, DESIGN.md section 3, profiles/r2_ab_strict_hybrid.jsonl); same bits either way
+            old_opt = rb._lib.set_option("strict_compact", -1)
             try:
                 o_ms, _, _ = timed(lambda: w.step(arith=other), 1, 1, before=w.reset)
             finally:
                 rb._lib.set_option("strict_compact", old_opt)
-            out["other_policies"]["values"]["strict_with_option_strict_compact_274"] = w.E_job * w.S / (o_ms * 1e-3)
+            out["other_policies"]["values"]["strict_thread_per_env (option strict_compact=-1)"] = w.E_job * w.S / (o_ms * 1e-3)
         if headline and name == "sphere_incline" and args.arith == "fast":
             def iso_step():
                 for _ in range(w.S // w.F):

@@ -28,7 +28,7 @@ for name in ("sphere_incline", "cube_bounce", "cube_incline"):
         kw = dict(restitution=0.2, friction_coeff=0.6, contact_threshold=1e-4)
     data = rb.BatchedData(model)
     ref = None
-    for compact, minb in ((-1, 2), (-1, 4), (-1, 5), (4, 0), (5, 0), (6, 0), (8, 0), (25, 0), (44, 0), (54, 0), (64, 0), (65, 0), (74, 0), (124, 0), (134, 0), (135, 0), (264, 0), (274, 0)):   # the instantiations kept in the library
+    for compact, minb in ((-1, 2), (-1, 4), (-1, 5), (4, 0), (5, 0), (6, 0), (8, 0), (25, 0), (44, 0), (54, 0), (64, 0), (65, 0), (74, 0), (124, 0), (134, 0), (135, 0), (264, 0), (274, 0), (364, 0), (374, 0), (0, 0)):   # the instantiations kept in the library
         rb._lib.set_option("strict_compact", compact)
         rb._lib.set_option("strict_minb", minb)
         best = None

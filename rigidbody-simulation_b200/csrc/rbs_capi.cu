@@ -220,9 +220,14 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
             // in registers (measured slower), 5x-8x = K environments per thread RESIDENT IN SHARED MEMORY (uniform mass / size /
             // inertia), 0 = where it measured faster (profiles/r2_ab_strict.jsonl, r2_ab_strict_resident.jsonl: sphere 2.28e10 ->
             // 2.56e10 compacted at 5 CTAs -> 3.60e10 resident at K = 3, 4 CTAs; cube 1.02e10 -> 7.7e9 / 1.08e10 / 6.6e9 (incline),
-            // so boxes stay on the thread-per-environment kernel).
+            // so boxes stayed on the thread-per-environment kernel until the rolled hybrid below).
             long compact = option("strict_compact");
-            if (compact == 0) compact = GEOM == 0 ? ((!a->mass && !a->size && !a->inertia) ? 64 : 5) : -1;
+            // boxes: the rolled K = 4 resident kernel whose dense CTAs take the thread-per-environment loop (374: cube bounce
+            // 1.32e10 -> 1.64e10, incline 9.6e9 -> 8.7e9 at 1M environments -- 512 environments per CTA are 3.5 waves there --
+            // profiles/r2_ab_strict_hybrid.jsonl); short launches and batches that would not fill the GPU with 512-environment CTAs
+            // keep the thread-per-environment kernel
+            if (compact == 0) compact = GEOM == 0 ? ((!a->mass && !a->size && !a->inertia) ? 64 : 5)
+                                                  : ((!a->mass && !a->size && !a->inertia && a->substeps >= 16 && w.cnt >= (1L << 18)) ? 374 : -1);
             if (!a->xfrc && compact >= 50 && !a->mass && !a->size && !a->inertia) {
                 // state resident in shared memory, K environments per thread: compact = 50 + 10*(K - 2) + resident CTAs, K = 2..4
 #define RBS_RES(KK, MB, WP, ...)                                                                                              \
@@ -242,6 +247,8 @@ template <typename T, int GEOM, int SCHEME> void launch_body_plane_iso(const rbs
                     case 264: RBS_RES(3, 4, false, true); return;     // 2KM: phases A and C as rolled loops over the K columns (cube bounce:
                                                                       // 1.56 / 1.63e10 at 264 / 274 against 1.32e10 thread-per-env; incline and sphere slower)
                     case 274: RBS_RES(4, 4, false, true); return;
+                    case 364: RBS_RES(3, 4, false, true, true); return;     // 3KM: rolled, and dense CTAs take the thread-per-environment loop
+                    case 374: RBS_RES(4, 4, false, true, true); return;
                     case 124: RBS_RES(2, 4, true); return;
                     case 134: RBS_RES(3, 4, true); return;
                     case 135: RBS_RES(3, 5, true); return;

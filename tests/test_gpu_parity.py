@@ -382,7 +382,7 @@ def test_strict_compaction_is_bit_identical(rb):
             rng = np.random.default_rng(4)
             e, mu, thr = rng.uniform(0.0, 0.5, E), rng.uniform(0.2, 0.9, E), 1e-4
         res = {}
-        for compact in (-1, 4, 5, 25, 44, 54, 64, 74, 124, 134, 264):   # 2x / 4x: K environments per thread in registers; 5x-7x: resident in shared memory; 1KM: one queue per warp
+        for compact in (-1, 4, 5, 25, 44, 54, 64, 74, 124, 134, 264, 374):   # 2x / 4x: K environments per thread in registers; 5x-7x: resident in shared memory; 1KM: one queue per warp
             old = rb._lib.set_option("strict_compact", compact)
             try:
                 model = build()
@@ -394,7 +394,7 @@ def test_strict_compaction_is_bit_identical(rb):
                 res[compact] = state_of(data) + tuple(c.copy() for c in data.counters())
             finally:
                 rb._lib.set_option("strict_compact", old)
-        for c in (4, 5, 25, 44, 54, 64, 74, 124, 134, 264):
+        for c in (4, 5, 25, 44, 54, 64, 74, 124, 134, 264, 374):
             for a, b in zip(res[-1], res[c]):
                 assert np.array_equal(a, b), (kind, E, dtype, c)
         assert res[4][2].sum() > E // 4                        # the horizon does exercise contacts
