@@ -59,6 +59,9 @@ RBS_API int rbs_device_count(void);
  * which kernel instantiation / launch shape computes it.  Every knob starts from the environment variable of the
  * same name in upper case with an RBS_ prefix (RBS_PF_MIN_SUBSTEPS ...).  Names: "minb", "pf_min_substeps",
  * "pf_packed", "strict_minb", "strict_compact", "strict_tb_minb", "strict_ms_regs", "box_minb", "box_compact", "tb_minb", "ms_skin_percent", "ms_kernel", "ms_walk_cost", "ms_tight_span", "ms_regs", "probe_mode", "host_chunks".
+ * "strict_compact" picks the strict single-body stepper: 0 = tuned (spheres: state resident in shared memory, contacts
+ * queued across the CTA; uniform boxes in large batches: the same with a per-CTA contact-density vote), -1 = one thread per
+ * environment throughout; the other codes are the A/B variants listed in DESIGN.md section 3 -- all give the same bits.
  * rbs_set_option returns RBS_EINVAL for an unknown name; rbs_get_option returns LONG_MIN for one. */
 RBS_API int rbs_set_option(const char *name, long value);
 RBS_API long rbs_get_option(const char *name);
